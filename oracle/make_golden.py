@@ -1,0 +1,93 @@
+"""Regenerate tests/golden/*.npz by running the UNMODIFIED reference (under oracle/shims) -- build container only.
+
+    python -m oracle.make_golden
+
+Inputs/weights/noise come from oracle.synth seeds (rebuildable anywhere); only the reference's OUTPUTS are
+stored.  Cases:
+  forward_small   ScorePosNet3D.forward, 2 graphs (60 protein + 9 / 7 ligand atoms), default config
+  chain_trunc     sample_diffusion, T=1000, num_steps=5 (t = 999..995: truncated chain, never reaches t==0)
+  chain_full_T20  sample_diffusion, num_diffusion_timesteps=20, num_steps=None (reaches the t==0 no-noise branch)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import refload, restate, synth  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+
+CASES = {
+    'forward_small': dict(cfg={}, weight_seed=0, batch=dict(seed=1, n_graphs=2, n_protein=60, ligand_sizes=[9, 7])),
+    'chain_trunc': dict(cfg={}, weight_seed=3, batch=dict(seed=2, n_graphs=2, n_protein=48, ligand_sizes=[8, 6]),
+                        tape_seed=7, num_steps=5),
+    'chain_full_T20': dict(cfg={'num_diffusion_timesteps': 20}, weight_seed=4,
+                           batch=dict(seed=5, n_graphs=1, n_protein=50, ligand_sizes=[10]), tape_seed=9, num_steps=None),
+}
+
+
+def build_reference_model(case):
+    ref = refload.import_reference()
+    cfg = refload.default_model_config()
+    cfg.update(case['cfg'])
+    model = ref.ScorePosNet3D(cfg, synth.PROTEIN_FEATURE_DIM, synth.LIGAND_NUM_CLASSES)
+    sd = synth.make_state_dict(case['weight_seed'], case['cfg'], schedules=restate.make_schedules(case['cfg']))
+    for k in synth.SCHEDULE_KEYS:       # our fp64->fp32 tables must equal the reference's own
+        assert torch.equal(model.state_dict()[k], sd[k]), k
+    model.load_state_dict(sd, strict=True)
+    return ref, model.eval(), sd
+
+
+def run_case(name):
+    case = CASES[name]
+    ref, model, sd = build_reference_model(case)
+    b = synth.make_batch(**case['batch'])
+    out = {}
+    with torch.no_grad():
+        if 'num_steps' not in case:
+            pp, lp, _ = ref.center_pos(b['protein_pos'], b['init_ligand_pos'], b['batch_protein'], b['batch_ligand'])
+            # capture the backbone's intermediate state through its own return_all / a forward hook
+            grabbed = {}
+            net = model.refine_net
+            orig = net._connect_edge
+            net._connect_edge = lambda x, m, bt: grabbed.setdefault('edge_index', orig(x, m, bt))
+            layer_out = []
+            hooks = [l.register_forward_hook(lambda mod, inp, o: layer_out.append((o[0].clone(), o[1].clone())))
+                     for l in net.base_block]
+            ew = []
+            hooks.append(net.edge_pred_layer.register_forward_hook(lambda mod, inp, o: ew.append(torch.sigmoid(o))))
+            preds = model(pp, b['protein_v'], b['batch_protein'], lp, b['init_ligand_v'], b['batch_ligand'])
+            for h in hooks:
+                h.remove()
+            net._connect_edge = orig
+            out = dict(pred_ligand_pos=preds['pred_ligand_pos'], pred_ligand_v=preds['pred_ligand_v'],
+                       final_h=preds['final_h'], edge_index=grabbed['edge_index'], e_w=ew[0].view(-1),
+                       layer_x=torch.stack([x for _, x in layer_out]), layer0_h=layer_out[0][0],
+                       layer4_h=layer_out[4][0])
+        else:
+            T = sd['betas'].shape[0]
+            S = case['num_steps'] or T
+            pn, vu = synth.make_tape(case['tape_seed'], S, len(b['batch_ligand']))
+            with refload.noise_tape(pn, vu):
+                r = model.sample_diffusion(b['protein_pos'], b['protein_v'], b['batch_protein'], b['init_ligand_pos'],
+                                           b['init_ligand_v'], b['batch_ligand'], num_steps=case['num_steps'],
+                                           center_pos_mode='protein')
+            out = dict(pos=r['pos'], v=r['v'], pos_traj=torch.stack(r['pos_traj']), v_traj=torch.stack(r['v_traj']),
+                       v0_traj=torch.stack(r['v0_traj']), vt_traj=torch.stack(r['vt_traj']))
+    return {k: v.detach().cpu().numpy() for k, v in out.items()}
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    for name in CASES:
+        arrs = run_case(name)
+        path = os.path.join(GOLDEN, name + '.npz')
+        np.savez_compressed(path, **arrs)
+        print(name, {k: v.shape for k, v in arrs.items()}, os.path.getsize(path), 'bytes')
+
+
+if __name__ == '__main__':
+    main()

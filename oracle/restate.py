@@ -1,0 +1,360 @@
+"""CPU restatement of targetdiff's denoising-sampling hot path (TEST INFRASTRUCTURE, see oracle/__init__.py).
+
+Plain torch-CPU fp32, op by op, working directly on a reference-layout `state_dict` (SURVEY.md
+Appendix D).  Every function cites the reference lines it restates (paths relative to /root/reference).
+Randomness never comes from an RNG here: the sampler consumes a *noise tape* (oracle.synth.make_tape)
+in the reference's draw order.
+
+Pinned against the reference itself (run under oracle/shims in the build container):
+tests/test_oracle_vs_reference.py (bit-exact) and the committed vectors in tests/golden/.
+Third-party arithmetic (torch_cluster knn, torch_scatter reduction order) is not in the reference
+tree -> "parity unpinned" there; canonical semantics per SURVEY.md Appendix A.3/A.4.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .synth import DEFAULT_MODEL_CONFIG, GAUSSIAN_OFFSETS
+
+
+# ----------------------------------------------------------------------------------------------
+# a14  schedules                                   models/molopt_score_model.py:48-97,169-170,221-267
+# ----------------------------------------------------------------------------------------------
+def _sigmoid_betas(beta_start, beta_end, T):
+    # models/molopt_score_model.py:72-74
+    b = np.linspace(-6, 6, T)
+    b = 1 / (np.exp(-b) + 1)
+    return b * (beta_end - beta_start) + beta_start
+
+
+def _cosine_alphas(T, s):
+    # models/molopt_score_model.py:80-97 (returns sqrt of the per-step alpha ratio, clipped)
+    steps = T + 1
+    x = np.linspace(0, steps, steps)
+    ac = np.cos(((x / steps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    alphas = ac[1:] / ac[:-1]
+    alphas = np.clip(alphas, a_min=0.001, a_max=1.)
+    return np.sqrt(alphas)
+
+
+def make_schedules(cfg=None):
+    """The 15 fp32 tables of ScorePosNet3D.__init__ (models/molopt_score_model.py:221-267).
+    fp64 numpy -> `.float()` exactly as `to_torch_const` (:104-107)."""
+    cfg = dict(DEFAULT_MODEL_CONFIG, **(cfg or {}))
+    T = cfg['num_diffusion_timesteps']
+    assert cfg['beta_schedule'] == 'sigmoid' and cfg['v_beta_schedule'] == 'cosine'
+    betas = _sigmoid_betas(cfg['beta_start'], cfg['beta_end'], T)
+    alphas = 1. - betas
+    ac = np.cumprod(alphas, axis=0)
+    ac_prev = np.append(1., ac[:-1])
+    f = lambda a: torch.from_numpy(np.asarray(a)).float()
+    out = {
+        'betas': f(betas), 'alphas_cumprod': f(ac), 'alphas_cumprod_prev': f(ac_prev),
+        'sqrt_alphas_cumprod': f(np.sqrt(ac)), 'sqrt_one_minus_alphas_cumprod': f(np.sqrt(1. - ac)),
+        'sqrt_recip_alphas_cumprod': f(np.sqrt(1. / ac)), 'sqrt_recipm1_alphas_cumprod': f(np.sqrt(1. / ac - 1)),
+        'posterior_mean_c0_coef': f(betas * np.sqrt(ac_prev) / (1. - ac)),
+        'posterior_mean_ct_coef': f((1. - ac_prev) * np.sqrt(alphas) / (1. - ac)),
+    }
+    post_var = f(betas * (1. - ac_prev) / (1. - ac))
+    out['posterior_var'] = post_var
+    # :254 -- note: built from the *fp32* tensor, index 0 replaced by index 1, log taken in fp32->fp64 numpy
+    out['posterior_logvar'] = f(np.log(np.append(post_var[1], post_var[1:])))
+    alphas_v = _cosine_alphas(T, cfg['v_beta_s'])
+    la = np.log(alphas_v)
+    lca = np.cumsum(la)
+    l1m = lambda a: np.log(1 - np.exp(a) + 1e-40)          # :169-170
+    out['log_alphas_v'] = f(la)
+    out['log_one_minus_alphas_v'] = f(l1m(la))
+    out['log_alphas_cumprod_v'] = f(lca)
+    out['log_one_minus_alphas_cumprod_v'] = f(l1m(lca))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# a13  categorical / posterior helpers             models/molopt_score_model.py:124-175,371-428,706-708
+# ----------------------------------------------------------------------------------------------
+def extract(coef, t, batch):
+    return coef[t][batch].unsqueeze(-1)                                    # :706-708
+
+
+def index_to_log_onehot(x, num_classes):
+    return torch.log(F.one_hot(x, num_classes).float().clamp(min=1e-30))   # :124-130
+
+
+def log_add_exp(a, b):
+    m = torch.max(a, b)                                                    # :173-175
+    return m + torch.log(torch.exp(a - m) + torch.exp(b - m))
+
+
+def q_v_pred_one_timestep(sd, log_vt_1, t, batch, K):
+    la = extract(sd['log_alphas_v'], t, batch)                             # :371-381
+    l1 = extract(sd['log_one_minus_alphas_v'], t, batch)
+    return log_add_exp(log_vt_1 + la, l1 - np.log(K))
+
+
+def q_v_pred(sd, log_v0, t, batch, K):
+    la = extract(sd['log_alphas_cumprod_v'], t, batch)                     # :383-392
+    l1 = extract(sd['log_one_minus_alphas_cumprod_v'], t, batch)
+    return log_add_exp(log_v0 + la, l1 - np.log(K))
+
+
+def q_v_posterior(sd, log_v0, log_vt, t, batch, K):
+    tm1 = t - 1                                                            # :401-409
+    tm1 = torch.where(tm1 < 0, torch.zeros_like(tm1), tm1)
+    un = q_v_pred(sd, log_v0, tm1, batch, K) + q_v_pred_one_timestep(sd, log_vt, t, batch, K)
+    return un - torch.logsumexp(un, dim=-1, keepdim=True)
+
+
+def q_pos_posterior(sd, x0, xt, t, batch):
+    return extract(sd['posterior_mean_c0_coef'], t, batch) * x0 + \
+        extract(sd['posterior_mean_ct_coef'], t, batch) * xt               # :424-428
+
+
+def log_sample_categorical_from_uniform(logits, uniform):
+    g = -torch.log(-torch.log(uniform + 1e-30) + 1e-30)                    # :160-166
+    return (g + logits).argmax(dim=-1)
+
+
+def center_pos(protein_pos, ligand_pos, batch_protein, batch_ligand, mode='protein'):
+    """models/molopt_score_model.py:110-120; scatter_mean = sequential sum / count."""
+    if mode == 'none':
+        return protein_pos, ligand_pos, 0.
+    assert mode == 'protein'
+    B = int(batch_protein.max()) + 1
+    s = torch.zeros(B, 3).index_add_(0, batch_protein, protein_pos)
+    cnt = torch.zeros(B).index_add_(0, batch_protein, torch.ones(len(batch_protein)))
+    cnt[cnt < 1] = 1
+    offset = s / cnt[:, None]
+    return protein_pos - offset[batch_protein], ligand_pos - offset[batch_ligand], offset
+
+
+# ----------------------------------------------------------------------------------------------
+# a8/a9  shared NN bits                                            models/common.py:7-26,60-90,156-162
+# ----------------------------------------------------------------------------------------------
+def gaussian_smearing(dist, offset):
+    coeff = -0.5 / (offset[1] - offset[0]).item() ** 2                     # common.py:17
+    d = dist.view(-1, 1) - offset.view(1, -1)                              # common.py:25
+    return torch.exp(coeff * torch.pow(d, 2))                              # common.py:26
+
+
+def outer_product_type_gauss(edge_type_onehot, g):
+    # common.py:83-90 for two vectors: out[e, t*20+j] = type[e,t]*g[e,j]  (int64 * f32 -> f32)
+    out = edge_type_onehot.unsqueeze(-1) * g.unsqueeze(1)
+    return out.view(out.shape[0], -1)
+
+
+def mlp(sd, prefix, x):
+    """Linear -> LayerNorm(eps=1e-5) -> ReLU -> Linear (common.py:60-80, norm=True, act_fn='relu')."""
+    y = F.linear(x, sd[prefix + '.net.0.weight'], sd[prefix + '.net.0.bias'])
+    y = F.layer_norm(y, (y.shape[-1],), sd[prefix + '.net.1.weight'], sd[prefix + '.net.1.bias'], 1e-5)
+    y = F.relu(y)
+    return F.linear(y, sd[prefix + '.net.3.weight'], sd[prefix + '.net.3.bias'])
+
+
+# ----------------------------------------------------------------------------------------------
+# a7  graph construction                                          models/uni_transformer.py:276-299
+# ----------------------------------------------------------------------------------------------
+def knn_graph_canonical(x, k, batch):
+    """Canonical k-NN: numpy, per graph, key = (fp32 d2, index) lexicographic.
+    d2 = ((dx*dx)+(dy*dy))+(dz*dz) with every op rounded to fp32.  Returns int64 [2,E] (row0 src, row1 dst)."""
+    xn = x.detach().cpu().numpy().astype(np.float32)
+    bn = batch.detach().cpu().numpy()
+    n = xn.shape[0]
+    src_all, dst_all = [], []
+    starts = np.flatnonzero(np.r_[True, bn[1:] != bn[:-1]]) if n else np.zeros(0, int)
+    ends = np.r_[starts[1:], n]
+    for s, e in zip(starts, ends):
+        xg = xn[s:e]
+        ng = e - s
+        dx = xg[:, None, 0] - xg[None, :, 0]
+        dy = xg[:, None, 1] - xg[None, :, 1]
+        dz = xg[:, None, 2] - xg[None, :, 2]
+        d2 = ((dx * dx).astype(np.float32) + (dy * dy).astype(np.float32)).astype(np.float32)
+        d2 = (d2 + (dz * dz).astype(np.float32)).astype(np.float32)
+        kk = min(k + 1, ng)
+        idx = np.arange(ng)
+        for i in range(ng):
+            order = np.lexsort((idx, d2[i]))[:kk]       # primary d2, secondary index
+            order = order[order != i]
+            src_all.append(order + s)
+            dst_all.append(np.full(len(order), i + s))
+    src = np.concatenate(src_all) if src_all else np.zeros(0, np.int64)
+    dst = np.concatenate(dst_all) if dst_all else np.zeros(0, np.int64)
+    return torch.from_numpy(np.stack([src, dst]).astype(np.int64))
+
+
+def build_edge_type(edge_index, mask_ligand):
+    """uni_transformer.py:288-299: L->L 0, L(src)->P(dst) 1, P(src)->L(dst) 2, P->P 3; one-hot int64 [E,4]."""
+    src, dst = edge_index
+    ns, nd = mask_ligand[src] == 1, mask_ligand[dst] == 1
+    code = torch.zeros(len(src), dtype=torch.long)
+    code[ns & nd] = 0
+    code[ns & ~nd] = 1
+    code[~ns & nd] = 2
+    code[~ns & ~nd] = 3
+    return F.one_hot(code, num_classes=4)
+
+
+# ----------------------------------------------------------------------------------------------
+# scatter ops in the reference's (CPU, sequential edge-order) semantics
+# ----------------------------------------------------------------------------------------------
+def scatter_softmax_rows(src, index, n):
+    """torch_scatter.composite.scatter_softmax over dim 0 (call sites uni_transformer.py:73,135)."""
+    idx = index[:, None].expand_as(src)
+    mx = torch.zeros(n, src.shape[1]).scatter_reduce(0, idx, src, reduce='amax', include_self=False)
+    ex = (src - mx.gather(0, idx)).exp_()
+    sm = torch.zeros(n, src.shape[1]).scatter_add_(0, idx, ex)
+    return ex.div(sm.gather(0, idx))
+
+
+def scatter_sum_rows(src, index, n):
+    """torch_scatter.scatter_sum over dim 0 (uni_transformer.py:78,139): scatter_add_ in edge order."""
+    idx = index.view(-1, *([1] * (src.dim() - 1))).expand_as(src)
+    return torch.zeros(n, *src.shape[1:]).scatter_add_(0, idx, src)
+
+
+# ----------------------------------------------------------------------------------------------
+# a10-a12  attention layers                                       models/uni_transformer.py:42-84,108-140,181-210
+# ----------------------------------------------------------------------------------------------
+def x2h_layer(sd, prefix, h, r_feat, edge_feat, edge_index, e_w, n_heads):
+    N = h.size(0)
+    src, dst = edge_index
+    kv_input = torch.cat([edge_feat, torch.cat([r_feat, h[dst], h[src]], -1)], -1)       # :45-51
+    H = h.shape[1]
+    k = mlp(sd, prefix + '.hk_func', kv_input).view(-1, n_heads, H // n_heads)           # :54
+    v = mlp(sd, prefix + '.hv_func', kv_input)                                           # :56
+    v = v * e_w.view(-1, 1)                                                              # :62-66
+    v = v.view(-1, n_heads, H // n_heads)
+    q = mlp(sd, prefix + '.hq_func', h).view(-1, n_heads, H // n_heads)                  # :70
+    alpha = scatter_softmax_rows((q[dst] * k / np.sqrt(k.shape[-1])).sum(-1), dst, N)    # :73-74
+    m = alpha.unsqueeze(-1) * v                                                          # :77
+    out = scatter_sum_rows(m, dst, N).view(-1, H)                                        # :78-79
+    return out + h                                                                       # :83 (out_fc=False)
+
+
+def h2x_layer(sd, prefix, h, rel_x, r_feat, edge_feat, edge_index, e_w, n_heads):
+    N = h.size(0)
+    src, dst = edge_index
+    kv_input = torch.cat([edge_feat, torch.cat([r_feat, h[dst], h[src]], -1)], -1)       # :111-117
+    H = h.shape[1]
+    k = mlp(sd, prefix + '.xk_func', kv_input).view(-1, n_heads, H // n_heads)           # :119
+    v = mlp(sd, prefix + '.xv_func', kv_input)                                           # :120
+    v = v * e_w.view(-1, 1)                                                              # :125-129
+    v = v.unsqueeze(-1) * rel_x.unsqueeze(1)                                             # :131
+    q = mlp(sd, prefix + '.xq_func', h).view(-1, n_heads, H // n_heads)                  # :132
+    alpha = scatter_softmax_rows((q[dst] * k / np.sqrt(k.shape[-1])).sum(-1), dst, N)    # :135
+    m = alpha.unsqueeze(-1) * v                                                          # :138
+    return scatter_sum_rows(m, dst, N).mean(1)                                           # :139-140
+
+
+def att_layer(sd, prefix, h, x, edge_type, edge_index, mask_ligand, e_w, n_heads, fix_x=False):
+    """AttentionLayerO2TwoUpdateNodeGeneral.forward, num_x2h=num_h2x=1, sync_twoup=False (:181-210)."""
+    src, dst = edge_index
+    offset = sd[prefix + '.distance_expansion.offset']
+    rel_x = x[dst] - x[src]                                                              # :188
+    dist = torch.norm(rel_x, p=2, dim=-1, keepdim=True)                                  # :189
+    r_feat = outer_product_type_gauss(edge_type, gaussian_smearing(dist, offset))        # :194-195
+    h_out = x2h_layer(sd, prefix + '.x2h_layers.0', h, r_feat, edge_type, edge_index, e_w, n_heads)
+    r_feat = outer_product_type_gauss(edge_type, gaussian_smearing(dist, offset))        # :202-203
+    dx = h2x_layer(sd, prefix + '.h2x_layers.0', h_out, rel_x, r_feat, edge_type, edge_index, e_w, n_heads)
+    if not fix_x:
+        x = x + dx * mask_ligand[:, None]                                                # :205-206
+    return h_out, x
+
+
+def refine_net(sd, cfg, h, x, mask_ligand, batch, fix_x=False, edge_index=None, trace=None):
+    """UniTransformerO2TwoUpdateGeneral.forward (uni_transformer.py:301-328), num_blocks=1, knn, ew 'global'."""
+    assert cfg['num_blocks'] == 1 and cfg['cutoff_mode'] == 'knn' and cfg['ew_net_type'] == 'global'
+    if edge_index is None:
+        edge_index = knn_graph_canonical(x, cfg['knn'], batch)                           # :307
+    src, dst = edge_index
+    edge_type = build_edge_type(edge_index, mask_ligand)                                 # :311
+    dist = torch.norm(x[dst] - x[src], p=2, dim=-1, keepdim=True)                        # :313
+    dist_feat = gaussian_smearing(dist, sd['refine_net.distance_expansion.offset'])      # :314
+    e_w = torch.sigmoid(mlp(sd, 'refine_net.edge_pred_layer', dist_feat))                # :315-316
+    if trace is not None:
+        trace.update(edge_index=edge_index, edge_type=edge_type.argmax(-1), e_w=e_w.view(-1), all_h=[h], all_x=[x])
+    for l in range(cfg['num_layers']):
+        h, x = att_layer(sd, 'refine_net.base_block.%d' % l, h, x, edge_type, edge_index, mask_ligand, e_w,
+                         cfg['n_heads'], fix_x=fix_x)                                    # :320-321
+        if trace is not None:
+            trace['all_h'].append(h)
+            trace['all_x'].append(x)
+    return {'x': x, 'h': h}
+
+
+# ----------------------------------------------------------------------------------------------
+# a5/a6  forward                               models/molopt_score_model.py:313-368; models/common.py:120-137
+# ----------------------------------------------------------------------------------------------
+def compose_context(h_protein, h_ligand, pos_protein, pos_ligand, batch_protein, batch_ligand):
+    batch_ctx = torch.cat([batch_protein, batch_ligand], dim=0)
+    sort_idx = torch.sort(batch_ctx, stable=True).indices                                # common.py:126
+    mask_ligand = torch.cat([torch.zeros(len(batch_protein)).bool(), torch.ones(len(batch_ligand)).bool()])[sort_idx]
+    return (torch.cat([h_protein, h_ligand])[sort_idx], torch.cat([pos_protein, pos_ligand])[sort_idx],
+            batch_ctx[sort_idx], mask_ligand)
+
+
+def forward(sd, cfg, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v, batch_ligand,
+            fix_x=False, trace=None):
+    """ScorePosNet3D.forward with time_emb_dim=0, node_indicator=True (molopt_score_model.py:313-368)."""
+    cfg = dict(DEFAULT_MODEL_CONFIG, **(cfg or {}))
+    assert cfg['time_emb_dim'] == 0 and cfg['node_indicator']
+    K = sd['ligand_atom_emb.weight'].shape[1]
+    lig_feat = F.one_hot(ligand_v, K).float()                                            # :317
+    h_p = F.linear(protein_v, sd['protein_atom_emb.weight'], sd['protein_atom_emb.bias'])  # :333
+    h_l = F.linear(lig_feat, sd['ligand_atom_emb.weight'], sd['ligand_atom_emb.bias'])     # :334
+    h_p = torch.cat([h_p, torch.zeros(len(h_p), 1)], -1)                                 # :336-338
+    h_l = torch.cat([h_l, torch.ones(len(h_l), 1)], -1)
+    h_all, pos_all, batch_all, mask_ligand = compose_context(h_p, h_l, protein_pos, ligand_pos, batch_protein, batch_ligand)
+    out = refine_net(sd, cfg, h_all, pos_all, mask_ligand, batch_all, fix_x=fix_x, trace=trace)   # :349
+    final_pos, final_h = out['x'], out['h']
+    lig_h = final_h[mask_ligand]                                                         # :350-351
+    y = F.linear(lig_h, sd['v_inference.0.weight'], sd['v_inference.0.bias'])            # :307-311,352
+    y = F.softplus(y) - torch.log(torch.tensor(2.0)).item()     # common.py:156-162 (shift = fp32 log 2)
+    logits = F.linear(y, sd['v_inference.2.weight'], sd['v_inference.2.bias'])
+    if trace is not None:
+        trace.update(mask_ligand=mask_ligand, batch_all=batch_all)
+    return {'pred_ligand_pos': final_pos[mask_ligand], 'pred_ligand_v': logits, 'final_h': final_h,
+            'final_ligand_h': lig_h}
+
+
+# ----------------------------------------------------------------------------------------------
+# a4  the sampling loop                                        models/molopt_score_model.py:633-703
+# ----------------------------------------------------------------------------------------------
+def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand_pos, init_ligand_v, batch_ligand,
+                     pos_noise, v_uniform, num_steps=None, center_pos_mode='protein', step_callback=None):
+    """C0-mode sampler driven by a noise tape: pos_noise [S,Nl,3], v_uniform [S,Nl,K].
+    Returns the reference's dict ('pos','v','pos_traj','v_traj','v0_traj','vt_traj'), trajectories as lists."""
+    cfg = dict(DEFAULT_MODEL_CONFIG, **(cfg or {}))
+    assert cfg['model_mean_type'] == 'C0'
+    T = sd['betas'].shape[0]
+    K = sd['ligand_atom_emb.weight'].shape[1]
+    if num_steps is None:
+        num_steps = T
+    num_graphs = int(batch_protein.max()) + 1
+    protein_pos, ligand_pos, offset = center_pos(protein_pos, init_ligand_pos, batch_protein, batch_ligand, center_pos_mode)
+    ligand_v = init_ligand_v
+    pos_traj, v_traj, v0_traj, vt_traj = [], [], [], []
+    time_seq = list(reversed(range(T - num_steps, T)))                                   # :649
+    for s, i in enumerate(time_seq):
+        t = torch.full((num_graphs,), i, dtype=torch.long)                               # :651
+        preds = forward(sd, cfg, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v, batch_ligand)
+        pos0, v0 = preds['pred_ligand_pos'], preds['pred_ligand_v']                      # :667-669
+        pos_mean = q_pos_posterior(sd, pos0, ligand_pos, t, batch_ligand)                # :673
+        logvar = extract(sd['posterior_logvar'], t, batch_ligand)                        # :674
+        nonzero = (1 - (t == 0).float())[batch_ligand].unsqueeze(-1)                     # :676
+        ligand_pos = pos_mean + nonzero * (0.5 * logvar).exp() * pos_noise[s]            # :677-679
+        log_v_recon = F.log_softmax(v0, dim=-1)                                          # :682
+        log_v = index_to_log_onehot(ligand_v, K)                                         # :683
+        log_model_prob = q_v_posterior(sd, log_v_recon, log_v, t, batch_ligand, K)       # :684
+        ligand_v = log_sample_categorical_from_uniform(log_model_prob, v_uniform[s])     # :685
+        v0_traj.append(log_v_recon.clone()); vt_traj.append(log_model_prob.clone())      # :687-688
+        pos_traj.append((ligand_pos + offset[batch_ligand]).clone())                     # :691-692
+        v_traj.append(ligand_v.clone())                                                  # :693
+        if step_callback is not None:
+            step_callback(s, i, preds, ligand_pos, ligand_v)
+    return {'pos': ligand_pos + offset[batch_ligand], 'v': ligand_v, 'pos_traj': pos_traj, 'v_traj': v_traj,
+            'v0_traj': v0_traj, 'vt_traj': vt_traj}

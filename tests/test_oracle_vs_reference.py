@@ -1,0 +1,89 @@
+"""Pins oracle/restate.py against the UNMODIFIED reference (run under oracle/shims).  Build container only:
+skipped where /root/reference is absent (the GPU box) -- the committed tests/golden/ vectors carry the pin there."""
+import pytest
+import torch
+
+from oracle import refload, restate, synth
+
+pytestmark = pytest.mark.skipif(not refload.reference_available(), reason='reference tree not present')
+
+
+@pytest.fixture(scope='module')
+def ref_model():
+    ref = refload.import_reference()
+    cfg = refload.default_model_config()
+    model = ref.ScorePosNet3D(cfg, synth.PROTEIN_FEATURE_DIM, synth.LIGAND_NUM_CLASSES).eval()
+    return ref, model
+
+
+def test_state_dict_layout_matches_reference(ref_model):
+    _, model = ref_model
+    sd = model.state_dict()
+    spec = synth.state_dict_spec()
+    assert list(sd.keys()) == [k for k, _, _ in spec]
+    for k, shape, _ in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert len(spec) == 384
+
+
+def test_schedules_bit_exact(ref_model):
+    _, model = ref_model
+    sched = restate.make_schedules()
+    for k in synth.SCHEDULE_KEYS:
+        assert torch.equal(model.state_dict()[k], sched[k]), k
+
+
+def test_knn_shim_equals_canonical_restatement():
+    from torch_geometric.nn import knn_graph  # the shim
+    b = synth.make_batch(11, 3, n_protein=70, ligand_sizes=[5, 9, 1])
+    x = torch.cat([b['protein_pos'], b['init_ligand_pos']])
+    batch = torch.cat([b['batch_protein'], b['batch_ligand']])
+    order = torch.sort(batch, stable=True).indices
+    x, batch = x[order], batch[order]
+    for k in (8, 32, 48):
+        assert torch.equal(knn_graph(x, k=k, batch=batch, flow='source_to_target'), restate.knn_graph_canonical(x, k, batch))
+
+
+def test_knn_small_graph_and_ties():
+    from torch_geometric.nn import knn_graph
+    # graph 0 has 5 nodes (< k+1) incl. exact duplicate points and equidistant neighbours; graph 1 has 40 on a lattice
+    g0 = torch.tensor([[0., 0, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 0], [0, 1, 0]])
+    g1 = torch.stack(torch.meshgrid(torch.arange(5.), torch.arange(4.), torch.arange(2.), indexing='ij'), -1).reshape(-1, 3)
+    x = torch.cat([g0, g1])
+    batch = torch.cat([torch.zeros(5, dtype=torch.long), torch.ones(40, dtype=torch.long)])
+    a = knn_graph(x, k=32, batch=batch)
+    b = restate.knn_graph_canonical(x, 32, batch)
+    assert torch.equal(a, b)
+    assert (a[1] < 5).sum() == 5 * 4              # fewer than k edges per node in the small graph
+    assert ((a[1] >= 5).sum()) == 40 * 32
+
+
+def test_forward_bit_exact(ref_model):
+    ref, model = ref_model
+    sd = synth.make_state_dict(0, schedules=restate.make_schedules())
+    model.load_state_dict(sd, strict=True)
+    b = synth.make_batch(1, 2, n_protein=60, ligand_sizes=[9, 7])
+    with torch.no_grad():
+        pp, lp, _ = ref.center_pos(b['protein_pos'], b['init_ligand_pos'], b['batch_protein'], b['batch_ligand'])
+        want = model(pp, b['protein_v'], b['batch_protein'], lp, b['init_ligand_v'], b['batch_ligand'])
+    pp2, lp2, _ = restate.center_pos(b['protein_pos'], b['init_ligand_pos'], b['batch_protein'], b['batch_ligand'])
+    assert torch.equal(pp, pp2) and torch.equal(lp, lp2)
+    got = restate.forward(sd, None, pp2, b['protein_v'], b['batch_protein'], lp2, b['init_ligand_v'], b['batch_ligand'])
+    for k in ('pred_ligand_pos', 'pred_ligand_v', 'final_h', 'final_ligand_h'):
+        assert torch.equal(want[k], got[k]), k
+
+
+def test_sampling_chain_bit_exact(ref_model):
+    _, model = ref_model
+    sd = synth.make_state_dict(3, schedules=restate.make_schedules())
+    model.load_state_dict(sd, strict=True)
+    b = synth.make_batch(2, 2, n_protein=48, ligand_sizes=[8, 6])
+    S = 3
+    pn, vu = synth.make_tape(7, S, len(b['batch_ligand']))
+    args = (b['protein_pos'], b['protein_v'], b['batch_protein'], b['init_ligand_pos'], b['init_ligand_v'], b['batch_ligand'])
+    with torch.no_grad(), refload.noise_tape(pn, vu):
+        want = model.sample_diffusion(*args, num_steps=S, center_pos_mode='protein')
+    got = restate.sample_diffusion(sd, None, *args, pn, vu, num_steps=S)
+    assert torch.equal(want['pos'], got['pos']) and torch.equal(want['v'], got['v'])
+    for k in ('pos_traj', 'v_traj', 'v0_traj', 'vt_traj'):
+        assert all(torch.equal(a, c) for a, c in zip(want[k], got[k])), k

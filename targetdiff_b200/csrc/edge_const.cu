@@ -1,0 +1,68 @@
+// edge_const.cu -- per-forward edge constants: 4-way edge type and the global edge gate e_w.
+//
+// Replaces (reference models/uni_transformer.py): _build_edge_type (:288-299) and the ew_net_type='global' gate
+// e_w = sigmoid(MLP(20->128->1)(GaussianSmearing(|x_dst - x_src|)))  (:312-316), both evaluated once per forward on
+// the forward's input coordinates and shared by all layers.
+// One warp per edge slot; the 20->128 first layer lives in shared memory (k-major), LayerNorm by warp shuffles.
+#include "tdiff_common.cuh"
+
+#define EC_WARPS 8
+
+__global__ void __launch_bounds__(EC_WARPS * 32)
+edge_const_kernel(const float4* __restrict__ xm, const int* __restrict__ src, long long n_slots, int k,
+                  const float* __restrict__ offsets, float coeff, const float* __restrict__ w1t, const float* __restrict__ b1,
+                  const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ w2, float b2,
+                  unsigned char* __restrict__ etype, float* __restrict__ e_w) {
+  __shared__ float s_w1t[TD_NG * TD_H];
+  __shared__ float s_b1[TD_H], s_g[TD_H], s_b[TD_H], s_w2[TD_H];
+  for (int i = threadIdx.x; i < TD_NG * TD_H; i += blockDim.x) s_w1t[i] = w1t[i];
+  for (int i = threadIdx.x; i < TD_H; i += blockDim.x) {
+    s_b1[i] = b1[i]; s_g[i] = ln_g[i]; s_b[i] = ln_b[i]; s_w2[i] = w2[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const float mu = offsets[lane < TD_NG ? lane : 0];
+  const long long warp0 = (long long)blockIdx.x * EC_WARPS + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * EC_WARPS;
+  for (long long e = warp0; e < n_slots; e += nwarps) {
+    const int s = src[e];
+    if (s < 0) {
+      if (lane == 0) { etype[e] = 3; e_w[e] = 0.0f; }
+      continue;
+    }
+    const int dst = (int)(e / k);
+    const float4 xd = xm[dst], xs = xm[s];
+    const float dx = xd.x - xs.x, dy = xd.y - xs.y, dz = xd.z - xs.z;
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float t = dist - mu;
+    const float gj = expf(coeff * (t * t));
+    float p[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) p[c] = s_b1[lane + 32 * c];
+#pragma unroll
+    for (int j = 0; j < TD_NG; ++j) {
+      const float g = __shfl_sync(0xffffffffu, gj, j);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) p[c] = fmaf(g, s_w1t[j * TD_H + lane + 32 * c], p[c]);
+    }
+    ln_relu_128(p, s_g, s_b, lane);
+    float acc = (p[0] * s_w2[lane] + p[1] * s_w2[lane + 32]) + (p[2] * s_w2[lane + 64] + p[3] * s_w2[lane + 96]);
+    acc = warp_sum(acc) + b2;
+    if (lane == 0) {
+      const bool ns = xs.w != 0.0f, nd = xd.w != 0.0f;
+      etype[e] = ns ? (nd ? 0 : 1) : (nd ? 2 : 3);
+      e_w[e] = 1.0f / (1.0f + expf(-acc));
+    }
+  }
+}
+
+void td_launch_edge_const(const float4* xm, const int* src, int n_nodes, int k, const float* offsets, float coeff,
+                          const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
+                          unsigned char* etype, float* e_w, cudaStream_t st) {
+  long long n_slots = (long long)n_nodes * k;
+  if (n_slots == 0) return;
+  long long blocks = (n_slots + EC_WARPS * 4 - 1) / (EC_WARPS * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  edge_const_kernel<<<(int)blocks, EC_WARPS * 32, 0, st>>>(xm, src, n_slots, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2,
+                                                            etype, e_w);
+}

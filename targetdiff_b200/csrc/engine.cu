@@ -1,0 +1,795 @@
+// engine.cu -- host side of libtdiff.so: the C-ABI of include/tdiff.h, weight re-packing, HBM layout, per-step
+// orchestration and CUDA-graph replay.  No torch, no CPU fallback: every entry point needs a CUDA device.
+//
+// HBM layout of a bound batch (N nodes in compose_context order, K = knn, Nl ligand atoms):
+//   xm[2]   float4 [N]      (x, y, z, is_ligand) ping-pong: protein rows identical in both, a layer writes the ligand
+//                           rows of the other buffer (models/uni_transformer.py:205-206 updates ligand atoms only)
+//   h, h0   fp32 [N,128]    node features / cached protein embedding (step-invariant, models/molopt_score_model.py:333)
+//   P       fp32 [N,640]    node projections of the split first layers [A_k | A_v | B_k | B_v | q_pre]
+//   q       fp32 [N,128]    query MLP output
+//   src     int32 [N*K]     dst-sorted neighbour slots (-1 = absent);  etype uint8 [N*K];  e_w fp32 [N*K]
+//   kbuf, vbuf fp32 [N*K,128]; v16 fp32 [Nl*K,16]   per-edge keys / values (h2x uses the first Nl*K rows of kbuf)
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/tdiff.h"
+#include "sampler.cuh"
+#include "tdiff_common.cuh"
+
+static thread_local char g_err[1024] = "";
+static int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t _e = (call);                                                                           \
+    if (_e != cudaSuccess) return set_err(TDIFF_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) { (void)cudaGetLastError(); if (cudaMalloc(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); return -1; } want = bytes; }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum { EV_AGG_H = 0, EV_AGG_X = 1, EV_EDGE_MLP = 2, EV_TOTAL = 3, EV_KINDS = 4 };
+struct EvPair { cudaEvent_t a, b; int kind; };
+
+struct tdiff_engine {
+  tdiff_config cfg;
+  int device = 0, sm_count = 148;
+  // ---- weights (one device arena)
+  float* arena = nullptr;
+  std::vector<TdLayer> layers;
+  const float *w_prot = nullptr, *b_prot = nullptr, *wl_t = nullptr, *bl = nullptr;
+  const float *ew_w1t = nullptr, *ew_b1 = nullptr, *ew_g = nullptr, *ew_b = nullptr, *ew_w2 = nullptr, *ew_off = nullptr;
+  float ew_b2 = 0.f, ew_coeff = -0.5f;
+  const float *hd_w1t = nullptr, *hd_b1 = nullptr, *hd_w2 = nullptr, *hd_b2 = nullptr;
+  const float *t_c0 = nullptr, *t_ct = nullptr, *t_logvar = nullptr, *t_la = nullptr, *t_l1ma = nullptr, *t_lca = nullptr, *t_l1mca = nullptr;
+  // ---- batch
+  bool bound = false, has_ligand = false, have_graph = false;
+  int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
+  DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
+  DevBuf xm0, xm1, offset, h0, h, P, q, src, etype, e_w, kbuf, vbuf, v16, lig_pos, lig_v, logits;
+  DevBuf step, err_flag, node_off, total_edges;
+  DevBuf stage[8];   // staging for tdiff_sample_host
+  // ---- instrumentation
+  long long launches = 0;
+  bool profiling = false;
+  std::vector<EvPair> events;
+  double ms_acc[EV_KINDS] = {0, 0, 0, 0};
+  long long n_acc[EV_KINDS] = {0, 0, 0, 0};
+};
+
+// ---------------------------------------------------------------------------------------------- weights
+namespace {
+struct Packer {
+  std::map<std::string, const tdiff_tensor*> byname;
+  std::vector<float> host;
+  std::string missing;
+  const float* get(const std::string& name, int64_t numel) {
+    auto it = byname.find(name);
+    if (it == byname.end() || it->second->numel != numel || it->second->data == nullptr) {
+      if (missing.empty()) missing = name + (it == byname.end() ? " (absent)" : " (wrong size)");
+      return nullptr;
+    }
+    return it->second->data;
+  }
+  size_t alloc(size_t n) {   // 256-byte aligned blocks
+    size_t off = (host.size() + 63) / 64 * 64;
+    host.resize(off + n, 0.0f);
+    return off;
+  }
+};
+
+struct MlpOff { size_t tab, ln_g, ln_b, w2t, b2; int nout; };
+
+// edge MLP: first Linear [128, 4 + 80 + 128 + 128] split, LayerNorm affine, second Linear transposed
+bool pack_edge_mlp(Packer& pk, const std::string& p, int nout, MlpOff& o, const float** w1_out) {
+  const int KV = 4 + 4 * TD_NG + 2 * TD_H;
+  const float* w1 = pk.get(p + ".net.0.weight", (int64_t)TD_H * KV);
+  const float* b1 = pk.get(p + ".net.0.bias", TD_H);
+  const float* g = pk.get(p + ".net.1.weight", TD_H);
+  const float* b = pk.get(p + ".net.1.bias", TD_H);
+  const float* w2 = pk.get(p + ".net.3.weight", (int64_t)nout * TD_H);
+  const float* b2 = pk.get(p + ".net.3.bias", nout);
+  if (!w1 || !b1 || !g || !b || !w2 || !b2) return false;
+  o.nout = nout;
+  o.tab = pk.alloc(4 * TD_TAB * TD_H);
+  for (int t = 0; t < 4; ++t) {
+    for (int j = 0; j < TD_NG; ++j)
+      for (int f = 0; f < TD_H; ++f) pk.host[o.tab + (t * TD_TAB + j) * TD_H + f] = w1[(size_t)f * KV + 4 + t * TD_NG + j];
+    for (int f = 0; f < TD_H; ++f) pk.host[o.tab + (t * TD_TAB + TD_NG) * TD_H + f] = w1[(size_t)f * KV + t] + b1[f];
+  }
+  o.ln_g = pk.alloc(TD_H); memcpy(&pk.host[o.ln_g], g, TD_H * sizeof(float));
+  o.ln_b = pk.alloc(TD_H); memcpy(&pk.host[o.ln_b], b, TD_H * sizeof(float));
+  o.w2t = pk.alloc((size_t)TD_H * nout);
+  for (int kk = 0; kk < TD_H; ++kk)
+    for (int n = 0; n < nout; ++n) pk.host[o.w2t + (size_t)kk * nout + n] = w2[(size_t)n * TD_H + kk];
+  o.b2 = pk.alloc(nout); memcpy(&pk.host[o.b2], b2, nout * sizeof(float));
+  *w1_out = w1;
+  return true;
+}
+
+struct SubOff { size_t wn_t, bn; MlpOff k, v, q; };
+
+bool pack_sublayer(Packer& pk, const std::string& p, const char* kn, const char* vn, const char* qn, int nout_v, SubOff& so) {
+  const int KV = 4 + 4 * TD_NG + 2 * TD_H;
+  const float *w1k = nullptr, *w1v = nullptr;
+  if (!pack_edge_mlp(pk, p + "." + kn, TD_H, so.k, &w1k)) return false;
+  if (!pack_edge_mlp(pk, p + "." + vn, nout_v, so.v, &w1v)) return false;
+  const std::string qp = p + "." + qn;
+  const float* w1q = pk.get(qp + ".net.0.weight", (int64_t)TD_H * TD_H);
+  const float* b1q = pk.get(qp + ".net.0.bias", TD_H);
+  const float* gq = pk.get(qp + ".net.1.weight", TD_H);
+  const float* bq = pk.get(qp + ".net.1.bias", TD_H);
+  const float* w2q = pk.get(qp + ".net.3.weight", (int64_t)TD_H * TD_H);
+  const float* b2q = pk.get(qp + ".net.3.bias", TD_H);
+  if (!w1q || !b1q || !gq || !bq || !w2q || !b2q) return false;
+  so.q.nout = TD_H; so.q.tab = 0;
+  so.q.ln_g = pk.alloc(TD_H); memcpy(&pk.host[so.q.ln_g], gq, TD_H * sizeof(float));
+  so.q.ln_b = pk.alloc(TD_H); memcpy(&pk.host[so.q.ln_b], bq, TD_H * sizeof(float));
+  so.q.w2t = pk.alloc((size_t)TD_H * TD_H);
+  for (int kk = 0; kk < TD_H; ++kk)
+    for (int n = 0; n < TD_H; ++n) pk.host[so.q.w2t + (size_t)kk * TD_H + n] = w2q[(size_t)n * TD_H + kk];
+  so.q.b2 = pk.alloc(TD_H); memcpy(&pk.host[so.q.b2], b2q, TD_H * sizeof(float));
+  so.wn_t = pk.alloc((size_t)TD_H * TD_NPROJ);
+  so.bn = pk.alloc(TD_NPROJ);
+  for (int kk = 0; kk < TD_H; ++kk) {
+    float* row = &pk.host[so.wn_t + (size_t)kk * TD_NPROJ];
+    for (int c = 0; c < TD_H; ++c) {
+      row[c] = w1k[(size_t)c * KV + 4 + 4 * TD_NG + kk];                 // A_k: h[dst] block of hk/xk
+      row[128 + c] = w1v[(size_t)c * KV + 4 + 4 * TD_NG + kk];           // A_v
+      row[256 + c] = w1k[(size_t)c * KV + 4 + 4 * TD_NG + TD_H + kk];    // B_k: h[src] block
+      row[384 + c] = w1v[(size_t)c * KV + 4 + 4 * TD_NG + TD_H + kk];    // B_v
+      row[512 + c] = w1q[(size_t)c * TD_H + kk];                         // q first Linear
+    }
+  }
+  for (int c = 0; c < TD_H; ++c) pk.host[so.bn + 512 + c] = b1q[c];
+  return true;
+}
+
+TdMlp mk_mlp(const float* base, const MlpOff& o, int offA, int offB) {
+  TdMlp m;
+  m.tab = base + o.tab; m.ln_g = base + o.ln_g; m.ln_b = base + o.ln_b; m.w2t = base + o.w2t; m.b2 = base + o.b2;
+  m.nout = o.nout; m.offA = offA; m.offB = offB;
+  return m;
+}
+}  // namespace
+
+extern "C" const char* tdiff_last_error(void) { return g_err; }
+extern "C" const char* tdiff_version(void) { return "tdiff-b200 0.1 (sm_100a)"; }
+
+extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int n_entries, int device, tdiff_engine** out) {
+  if (!cfg || !sd || !out) return set_err(TDIFF_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->hidden_dim != TD_H || cfg->n_heads != TD_HEADS || cfg->num_r_gaussian != TD_NG)
+    return set_err(TDIFF_EINVAL, "unsupported model shape: hidden_dim=%d n_heads=%d num_r_gaussian=%d (kernels are built for 128/16/20)",
+                   cfg->hidden_dim, cfg->n_heads, cfg->num_r_gaussian);
+  if (cfg->knn < 1 || cfg->knn > TD_KMAX) return set_err(TDIFF_EINVAL, "knn=%d outside 1..%d", cfg->knn, TD_KMAX);
+  if (cfg->num_layers < 1 || cfg->num_classes < 1 || cfg->num_classes > TD_CMAX || cfg->protein_feat_dim < 1 || cfg->num_timesteps < 1)
+    return set_err(TDIFF_EINVAL, "bad config (num_layers=%d num_classes=%d protein_feat_dim=%d num_timesteps=%d)", cfg->num_layers,
+                   cfg->num_classes, cfg->protein_feat_dim, cfg->num_timesteps);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    (void)cudaGetLastError();
+    return set_err(TDIFF_ECUDA, "no CUDA device: libtdiff has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return set_err(TDIFF_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return set_err(TDIFF_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+  tdiff_engine* e = new tdiff_engine();
+  e->cfg = *cfg; e->device = device; e->sm_count = prop.multiProcessorCount; e->K = cfg->knn;
+
+  Packer pk;
+  for (int i = 0; i < n_entries; ++i)
+    if (sd[i].name) pk.byname[sd[i].name] = &sd[i];
+  const int T = cfg->num_timesteps, KC = cfg->num_classes, F = cfg->protein_feat_dim, L = cfg->num_layers;
+  struct { const char* name; size_t off; } tabs[7] = {{"posterior_mean_c0_coef", 0}, {"posterior_mean_ct_coef", 0}, {"posterior_logvar", 0},
+      {"log_alphas_v", 0}, {"log_one_minus_alphas_v", 0}, {"log_alphas_cumprod_v", 0}, {"log_one_minus_alphas_cumprod_v", 0}};
+  for (auto& t : tabs) {
+    const float* p = pk.get(t.name, T);
+    t.off = pk.alloc(T);
+    if (p) memcpy(&pk.host[t.off], p, T * sizeof(float));
+  }
+  // embeddings
+  const float* wp = pk.get("protein_atom_emb.weight", (int64_t)(TD_H - 1) * F);
+  const float* bp = pk.get("protein_atom_emb.bias", TD_H - 1);
+  const float* wl = pk.get("ligand_atom_emb.weight", (int64_t)(TD_H - 1) * KC);
+  const float* blp = pk.get("ligand_atom_emb.bias", TD_H - 1);
+  size_t o_wp = pk.alloc((size_t)TD_H * F), o_bp = pk.alloc(TD_H), o_wl = pk.alloc((size_t)KC * TD_H), o_bl = pk.alloc(TD_H);
+  if (wp && bp && wl && blp) {
+    memcpy(&pk.host[o_wp], wp, (size_t)(TD_H - 1) * F * sizeof(float));
+    memcpy(&pk.host[o_bp], bp, (TD_H - 1) * sizeof(float));
+    for (int v = 0; v < KC; ++v)
+      for (int f = 0; f < TD_H - 1; ++f) pk.host[o_wl + (size_t)v * TD_H + f] = wl[(size_t)f * KC + v];
+    memcpy(&pk.host[o_bl], blp, (TD_H - 1) * sizeof(float));
+  }
+  // global edge gate (models/uni_transformer.py:242-243,312-316)
+  const float* gw1 = pk.get("refine_net.edge_pred_layer.net.0.weight", (int64_t)TD_H * TD_NG);
+  const float* gb1 = pk.get("refine_net.edge_pred_layer.net.0.bias", TD_H);
+  const float* gg = pk.get("refine_net.edge_pred_layer.net.1.weight", TD_H);
+  const float* gb = pk.get("refine_net.edge_pred_layer.net.1.bias", TD_H);
+  const float* gw2 = pk.get("refine_net.edge_pred_layer.net.3.weight", TD_H);
+  const float* gb2 = pk.get("refine_net.edge_pred_layer.net.3.bias", 1);
+  const float* goff = pk.get("refine_net.distance_expansion.offset", TD_NG);
+  size_t o_gw1 = pk.alloc((size_t)TD_NG * TD_H), o_gb1 = pk.alloc(TD_H), o_gg = pk.alloc(TD_H), o_gb = pk.alloc(TD_H), o_gw2 = pk.alloc(TD_H),
+         o_goff = pk.alloc(TD_NG);
+  if (gw1 && gb1 && gg && gb && gw2 && gb2 && goff) {
+    for (int j = 0; j < TD_NG; ++j)
+      for (int f = 0; f < TD_H; ++f) pk.host[o_gw1 + (size_t)j * TD_H + f] = gw1[(size_t)f * TD_NG + j];
+    memcpy(&pk.host[o_gb1], gb1, TD_H * 4); memcpy(&pk.host[o_gg], gg, TD_H * 4); memcpy(&pk.host[o_gb], gb, TD_H * 4);
+    memcpy(&pk.host[o_gw2], gw2, TD_H * 4); memcpy(&pk.host[o_goff], goff, TD_NG * 4);
+    e->ew_b2 = gb2[0];
+    const float d = goff[1] - goff[0];
+    e->ew_coeff = -0.5f / (d * d);
+  }
+  // head
+  const float* hw1 = pk.get("v_inference.0.weight", (int64_t)TD_H * TD_H);
+  const float* hb1 = pk.get("v_inference.0.bias", TD_H);
+  const float* hw2 = pk.get("v_inference.2.weight", (int64_t)KC * TD_H);
+  const float* hb2 = pk.get("v_inference.2.bias", KC);
+  size_t o_hw1 = pk.alloc((size_t)TD_H * TD_H), o_hb1 = pk.alloc(TD_H), o_hw2 = pk.alloc((size_t)KC * TD_H), o_hb2 = pk.alloc(KC);
+  if (hw1 && hb1 && hw2 && hb2) {
+    for (int kk = 0; kk < TD_H; ++kk)
+      for (int n = 0; n < TD_H; ++n) pk.host[o_hw1 + (size_t)kk * TD_H + n] = hw1[(size_t)n * TD_H + kk];
+    memcpy(&pk.host[o_hb1], hb1, TD_H * 4); memcpy(&pk.host[o_hw2], hw2, (size_t)KC * TD_H * 4); memcpy(&pk.host[o_hb2], hb2, KC * 4);
+  }
+  // attention layers
+  std::vector<SubOff> sx(L), sh(L);
+  std::vector<size_t> o_off(L);
+  std::vector<float> coeffs(L, -0.5f);
+  for (int l = 0; l < L; ++l) {
+    const std::string p = "refine_net.base_block." + std::to_string(l);
+    if (!pack_sublayer(pk, p + ".x2h_layers.0", "hk_func", "hv_func", "hq_func", TD_H, sx[l])) break;
+    if (!pack_sublayer(pk, p + ".h2x_layers.0", "xk_func", "xv_func", "xq_func", TD_HEADS, sh[l])) break;
+    const float* off = pk.get(p + ".distance_expansion.offset", TD_NG);
+    o_off[l] = pk.alloc(TD_NG);
+    if (off) {
+      memcpy(&pk.host[o_off[l]], off, TD_NG * 4);
+      const float d = off[1] - off[0];
+      coeffs[l] = -0.5f / (d * d);
+    }
+  }
+  if (!pk.missing.empty()) {
+    delete e;
+    return set_err(TDIFF_EWEIGHT, "state_dict entry %s", pk.missing.c_str());
+  }
+  const size_t bytes = pk.host.size() * sizeof(float);
+  if (cudaMalloc(&e->arena, bytes) != cudaSuccess) { delete e; return set_err(TDIFF_ECUDA, "cudaMalloc(%zu) for weights failed", bytes); }
+  if (cudaMemcpy(e->arena, pk.host.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(e->arena); delete e; return set_err(TDIFF_ECUDA, "weight upload failed");
+  }
+  const float* A = e->arena;
+  e->t_c0 = A + tabs[0].off; e->t_ct = A + tabs[1].off; e->t_logvar = A + tabs[2].off; e->t_la = A + tabs[3].off;
+  e->t_l1ma = A + tabs[4].off; e->t_lca = A + tabs[5].off; e->t_l1mca = A + tabs[6].off;
+  e->w_prot = A + o_wp; e->b_prot = A + o_bp; e->wl_t = A + o_wl; e->bl = A + o_bl;
+  e->ew_w1t = A + o_gw1; e->ew_b1 = A + o_gb1; e->ew_g = A + o_gg; e->ew_b = A + o_gb; e->ew_w2 = A + o_gw2; e->ew_off = A + o_goff;
+  e->hd_w1t = A + o_hw1; e->hd_b1 = A + o_hb1; e->hd_w2 = A + o_hw2; e->hd_b2 = A + o_hb2;
+  e->layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    TdLayer& ly = e->layers[l];
+    ly.offsets = A + o_off[l]; ly.coeff = coeffs[l];
+    ly.x2h.wn_t = A + sx[l].wn_t; ly.x2h.bn = A + sx[l].bn;
+    ly.x2h.k = mk_mlp(A, sx[l].k, 0, 256); ly.x2h.v = mk_mlp(A, sx[l].v, 128, 384); ly.x2h.q = mk_mlp(A, sx[l].q, 512, 512);
+    ly.h2x.wn_t = A + sh[l].wn_t; ly.h2x.bn = A + sh[l].bn;
+    ly.h2x.k = mk_mlp(A, sh[l].k, 0, 256); ly.h2x.v = mk_mlp(A, sh[l].v, 128, 384); ly.h2x.q = mk_mlp(A, sh[l].q, 512, 512);
+  }
+  if (e->step.ensure(sizeof(int)) || e->err_flag.ensure(sizeof(int)) || e->total_edges.ensure(sizeof(long long))) {
+    tdiff_destroy(e); return set_err(TDIFF_ECUDA, "cudaMalloc failed");
+  }
+  cudaMemset(e->err_flag.p, 0, sizeof(int));
+  *out = e;
+  return TDIFF_OK;
+}
+
+extern "C" void tdiff_destroy(tdiff_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (auto& ev : e->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  DevBuf* bufs[] = {&e->node_ptr, &e->prot_ptr, &e->prot_node, &e->prot_graph, &e->lig_node, &e->lig_graph, &e->node_lig, &e->xm0, &e->xm1,
+                    &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->etype, &e->e_w, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
+                    &e->lig_v, &e->logits, &e->step, &e->err_flag, &e->node_off, &e->total_edges};
+  for (auto* b : bufs) b->release();
+  for (auto& b : e->stage) b.release();
+  if (e->arena) cudaFree(e->arena);
+  delete e;
+}
+
+// ---------------------------------------------------------------------------------------------- batch binding
+extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const int32_t* lc, const float* d_ppos, const float* d_pfeat,
+                                int center_mode, void* stream) {
+  if (!e || !pc || !lc || B < 1) return set_err(TDIFF_EINVAL, "bind_batch: bad arguments");
+  if (center_mode != 0 && center_mode != 1) return set_err(TDIFF_EINVAL, "center_mode %d (0 'none' | 1 'protein')", center_mode);
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(e->device));
+  long long N = 0, Np = 0, Nl = 0;
+  int max_ng = 0;
+  for (int g = 0; g < B; ++g) {
+    if (pc[g] < 0 || lc[g] < 0) return set_err(TDIFF_EINVAL, "negative atom count in graph %d", g);
+    Np += pc[g]; Nl += lc[g];
+    if (pc[g] + lc[g] > max_ng) max_ng = pc[g] + lc[g];
+  }
+  N = Np + Nl;
+  if (N <= 0) return set_err(TDIFF_EINVAL, "empty batch");
+  if (N * (long long)e->K >= (1LL << 31) / 1) return set_err(TDIFF_EINVAL, "batch too large: N*k = %lld edge slots", N * e->K);
+  if (max_ng > 2800) return set_err(TDIFF_EINVAL, "graph with %d nodes exceeds the k-NN kernel's shared-memory tile (2800)", max_ng);
+  if (Np > 0 && (!d_ppos || !d_pfeat)) return set_err(TDIFF_EINVAL, "null protein arrays");
+  const int K = e->K;
+  std::vector<int> node_ptr(B + 1), prot_ptr(B + 1), prot_node(Np), prot_graph(Np), lig_node(Nl), lig_graph(Nl), node_lig(N, -1);
+  int n = 0, p = 0, a = 0;
+  for (int g = 0; g < B; ++g) {
+    node_ptr[g] = n; prot_ptr[g] = p;
+    for (int i = 0; i < pc[g]; ++i) { prot_node[p] = n; prot_graph[p] = g; ++p; ++n; }
+    for (int i = 0; i < lc[g]; ++i) { lig_node[a] = n; lig_graph[a] = g; node_lig[n] = a; ++a; ++n; }
+  }
+  node_ptr[B] = n; prot_ptr[B] = p;
+  e->bound = false; e->has_ligand = false; e->have_graph = false;
+  e->B = B; e->N = (int)N; e->Np = (int)Np; e->Nl = (int)Nl; e->max_ng = max_ng;
+  const size_t slots = (size_t)N * K;
+  int bad = 0;
+  bad |= e->node_ptr.ensure((B + 1) * 4) | e->prot_ptr.ensure((B + 1) * 4) | e->prot_node.ensure(Np * 4 + 4) | e->prot_graph.ensure(Np * 4 + 4);
+  bad |= e->lig_node.ensure(Nl * 4 + 4) | e->lig_graph.ensure(Nl * 4 + 4) | e->node_lig.ensure(N * 4);
+  bad |= e->xm0.ensure(N * 16) | e->xm1.ensure(N * 16) | e->offset.ensure((size_t)B * 16);
+  bad |= e->h0.ensure(N * TD_H * 4) | e->h.ensure(N * TD_H * 4) | e->P.ensure((size_t)N * TD_NPROJ * 4) | e->q.ensure(N * TD_H * 4);
+  bad |= e->src.ensure(slots * 4) | e->etype.ensure(slots) | e->e_w.ensure(slots * 4);
+  bad |= e->kbuf.ensure(slots * TD_H * 4) | e->vbuf.ensure(slots * TD_H * 4) | e->v16.ensure((size_t)Nl * K * TD_HEADS * 4 + 16);
+  bad |= e->lig_pos.ensure(Nl * 16 + 16) | e->lig_v.ensure(Nl * 4 + 4) | e->logits.ensure((size_t)Nl * e->cfg.num_classes * 4 + 4);
+  bad |= e->node_off.ensure(N * 8);
+  if (bad) return set_err(TDIFF_ECUDA, "out of device memory binding a batch of %lld nodes (%zu edge slots)", N, slots);
+  CK(cudaMemcpyAsync(e->node_ptr.p, node_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->prot_ptr.p, prot_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (Np) {
+    CK(cudaMemcpyAsync(e->prot_node.p, prot_node.data(), Np * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->prot_graph.p, prot_graph.data(), Np * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (Nl) {
+    CK(cudaMemcpyAsync(e->lig_node.p, lig_node.data(), Nl * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->lig_graph.p, lig_graph.data(), Nl * 4, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemcpyAsync(e->node_lig.p, node_lig.data(), N * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));   // host vectors go out of scope
+  CK(cudaMemsetAsync(e->offset.p, 0, (size_t)B * 16, st));
+  CK(cudaMemsetAsync(e->h0.p, 0, (size_t)N * TD_H * 4, st));
+  CK(cudaMemsetAsync(e->xm0.p, 0, (size_t)N * 16, st));
+  CK(cudaMemsetAsync(e->xm1.p, 0, (size_t)N * 16, st));
+  if (center_mode == 1) td_launch_segment_mean3(d_ppos, e->prot_ptr.as<int>(), B, e->offset.as<float4>(), st);
+  td_launch_place_protein(d_ppos, e->prot_node.as<int>(), e->prot_graph.as<int>(), e->offset.as<float4>(), (int)Np, e->xm0.as<float4>(),
+                          e->xm1.as<float4>(), st);
+  td_launch_protein_embed(d_pfeat, (int)Np, e->cfg.protein_feat_dim, e->w_prot, e->b_prot, e->prot_node.as<int>(), e->h0.as<float>(), st);
+  e->launches += 3;
+  CK(cudaGetLastError());
+  e->bound = true;
+  return TDIFF_OK;
+}
+
+extern "C" int tdiff_set_ligand(tdiff_engine* e, const float* d_pos, const int64_t* d_v, int apply_center, void* stream) {
+  if (!e || !e->bound) return set_err(TDIFF_ESTATE, "set_ligand before bind_batch");
+  if (e->Nl > 0 && !d_pos) return set_err(TDIFF_EINVAL, "null ligand positions");
+  if (!e->has_ligand && e->Nl > 0 && !d_v) return set_err(TDIFF_EINVAL, "ligand types required on first set_ligand");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(e->device));
+  td_launch_set_ligand(d_pos, (const long long*)d_v, e->lig_graph.as<int>(), e->offset.as<float4>(), apply_center, e->Nl,
+                       e->cfg.num_classes, e->lig_pos.as<float4>(), e->lig_v.as<int>(), e->err_flag.as<int>(), st);
+  e->launches += 1;
+  if (d_v) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, e->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (flag) {
+      cudaMemsetAsync(e->err_flag.p, 0, sizeof(int), st);
+      return set_err(TDIFF_EINVAL, "ligand atom type index >= num_classes (%d)", e->cfg.num_classes);
+    }
+  }
+  CK(cudaGetLastError());
+  e->has_ligand = true;
+  return TDIFF_OK;
+}
+
+extern "C" int tdiff_get_ligand(tdiff_engine* e, float* d_pos, int64_t* d_v, int add_offset, void* stream) {
+  if (!e || !e->has_ligand) return set_err(TDIFF_ESTATE, "get_ligand before set_ligand");
+  CK(cudaSetDevice(e->device));
+  td_launch_get_ligand(e->lig_pos.as<float4>(), e->lig_v.as<int>(), e->lig_graph.as<int>(), e->offset.as<float4>(), add_offset, e->Nl, d_pos,
+                       (long long*)d_v, (cudaStream_t)stream);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return TDIFF_OK;
+}
+
+extern "C" int tdiff_get_offset(tdiff_engine* e, float* d_offset, void* stream) {
+  if (!e || !e->bound || !d_offset) return set_err(TDIFF_ESTATE, "get_offset before bind_batch");
+  CK(cudaSetDevice(e->device));
+  td_launch_gather_xyz(e->offset.as<float4>(), nullptr, e->B, d_offset, (cudaStream_t)stream);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return TDIFF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+namespace {
+struct Prof {
+  tdiff_engine* e; cudaStream_t st; int kind; bool on; EvPair ev;
+  Prof(tdiff_engine* e_, cudaStream_t st_, int kind_) : e(e_), st(st_), kind(kind_), on(e_->profiling) {
+    if (on) { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); ev.kind = kind; cudaEventRecord(ev.a, st); }
+  }
+  ~Prof() { if (on) { cudaEventRecord(ev.b, st); e->events.push_back(ev); } }
+};
+
+// One evaluation of the network on the bound batch (reference ScorePosNet3D.forward -> UniTransformerO2TwoUpdateGeneral.forward)
+void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
+  const int N = e->N, Nl = e->Nl, K = e->K;
+  float4* xm[2] = {e->xm0.as<float4>(), e->xm1.as<float4>()};
+  const int* src = e->src.as<int>();
+  const unsigned char* etype = e->etype.as<unsigned char>();
+  float* h = e->h.as<float>();
+  float* P = e->P.as<float>();
+  float* q = e->q.as<float>();
+  td_launch_scatter_ligand_pos(e->lig_pos.as<float4>(), e->lig_node.as<int>(), Nl, xm[0], st);
+  td_launch_init_h(e->h0.as<float>(), xm[0], e->lig_v.as<int>(), e->node_lig.as<int>(), e->wl_t, e->bl, N, h, st);
+  td_launch_knn(xm[0], e->node_ptr.as<int>(), e->B, e->max_ng, K, e->src.as<int>(), st);
+  td_launch_edge_const(xm[0], src, N, K, e->ew_off, e->ew_coeff, e->ew_w1t, e->ew_b1, e->ew_g, e->ew_b, e->ew_w2, e->ew_b2,
+                       e->etype.as<unsigned char>(), e->e_w.as<float>(), st);
+  e->launches += 4;
+  int cur = 0;
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    const TdLayer& ly = e->layers[l];
+    // ---- x2h: h <- h + sum_e alpha * v * e_w
+    td_launch_node_proj(h, N, ly.x2h.wn_t, ly.x2h.bn, P, st);
+    td_launch_node_q(P, N, ly.x2h.q, q, st);
+    {
+      Prof pr(e, st, EV_EDGE_MLP);
+      td_launch_edge_mlp(P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), e->sm_count, st);
+      td_launch_edge_mlp(P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), e->sm_count, st);
+    }
+    {
+      Prof pr(e, st, EV_AGG_H);
+      td_launch_aggregate_h(e->kbuf.as<float>(), e->vbuf.as<float>(), e->e_w.as<float>(), src, q, h, h, N, K, st);
+    }
+    e->launches += 5;
+    if (fix_x || Nl == 0) continue;     // h2x only moves ligand atoms; with fix_x its result is discarded (:204-206)
+    // ---- h2x: x_lig <- x_lig + mean_heads sum_e alpha * v * e_w * (x_dst - x_src), destinations = ligand atoms only
+    td_launch_node_proj(h, N, ly.h2x.wn_t, ly.h2x.bn, P, st);
+    td_launch_node_q(P, N, ly.h2x.q, q, st);
+    {
+      Prof pr(e, st, EV_EDGE_MLP);
+      td_launch_edge_mlp(P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.k, ly.offsets, ly.coeff, e->kbuf.as<float>(),
+                         e->sm_count, st);
+      td_launch_edge_mlp(P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.v, ly.offsets, ly.coeff, e->v16.as<float>(),
+                         e->sm_count, st);
+    }
+    {
+      Prof pr(e, st, EV_AGG_X);
+      td_launch_aggregate_x(e->kbuf.as<float>(), e->v16.as<float>(), e->e_w.as<float>(), src, q, xm[cur], e->lig_node.as<int>(), xm[cur ^ 1], Nl, K, st);
+    }
+    e->launches += 5;
+    cur ^= 1;
+  }
+  td_launch_head(h, e->lig_node.as<int>(), Nl, e->hd_w1t, e->hd_b1, e->hd_w2, e->hd_b2, e->cfg.num_classes, e->logits.as<float>(), st);
+  e->launches += 1;
+  e->final_buf = cur;
+  e->have_graph = true;
+}
+}  // namespace
+
+extern "C" int tdiff_forward(tdiff_engine* e, float* d_pred_pos, float* d_pred_logits, float* d_final_h, int fix_x, void* stream) {
+  if (!e || !e->bound || !e->has_ligand) return set_err(TDIFF_ESTATE, "forward needs bind_batch + set_ligand first");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(e->device));
+  Prof* total = new Prof(e, st, EV_TOTAL);
+  run_forward(e, st, fix_x);
+  delete total;
+  const float4* xf = e->final_buf ? e->xm1.as<float4>() : e->xm0.as<float4>();
+  if (d_pred_pos) { td_launch_gather_xyz(xf, e->lig_node.as<int>(), e->Nl, d_pred_pos, st); e->launches += 1; }
+  if (d_pred_logits && e->Nl) CK(cudaMemcpyAsync(d_pred_logits, e->logits.p, (size_t)e->Nl * e->cfg.num_classes * 4, cudaMemcpyDeviceToDevice, st));
+  if (d_final_h) CK(cudaMemcpyAsync(d_final_h, e->h.p, (size_t)e->N * TD_H * 4, cudaMemcpyDeviceToDevice, st));
+  CK(cudaGetLastError());
+  return TDIFF_OK;
+}
+
+extern "C" int64_t tdiff_num_edges(tdiff_engine* e, void* stream) {
+  if (!e || !e->have_graph) return set_err(TDIFF_ESTATE, "no graph built yet (run forward first)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaSetDevice(e->device) != cudaSuccess) return set_err(TDIFF_ECUDA, "cudaSetDevice failed");
+  td_launch_edge_count_scan(e->src.as<int>(), e->N, e->K, e->node_off.as<long long>(), e->total_edges.as<long long>(), st);
+  e->launches += 1;
+  long long tot = 0;
+  if (cudaMemcpyAsync(&tot, e->total_edges.p, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    return set_err(TDIFF_ECUDA, "num_edges: %s", cudaGetErrorString(cudaGetLastError()));
+  return tot;
+}
+
+extern "C" int tdiff_get_edge_index(tdiff_engine* e, int64_t* d_edge_index, void* stream) {
+  if (!e || !e->have_graph || !d_edge_index) return set_err(TDIFF_ESTATE, "no graph built yet (run forward first)");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(e->device));
+  td_launch_edge_count_scan(e->src.as<int>(), e->N, e->K, e->node_off.as<long long>(), e->total_edges.as<long long>(), st);
+  td_launch_edge_compact(e->src.as<int>(), nullptr, e->N, e->K, e->node_off.as<long long>(), e->total_edges.as<long long>(),
+                         (long long*)d_edge_index, nullptr, st);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  return TDIFF_OK;
+}
+
+extern "C" int tdiff_get_edge_weight(tdiff_engine* e, float* d_e_w, void* stream) {
+  if (!e || !e->have_graph || !d_e_w) return set_err(TDIFF_ESTATE, "no graph built yet (run forward first)");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(e->device));
+  td_launch_edge_count_scan(e->src.as<int>(), e->N, e->K, e->node_off.as<long long>(), e->total_edges.as<long long>(), st);
+  td_launch_edge_compact(e->src.as<int>(), e->e_w.as<float>(), e->N, e->K, e->node_off.as<long long>(), e->total_edges.as<long long>(), nullptr,
+                         d_e_w, st);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  return TDIFF_OK;
+}
+
+extern "C" int tdiff_get_node_pos(tdiff_engine* e, float* d_x, void* stream) {
+  if (!e || !e->have_graph || !d_x) return set_err(TDIFF_ESTATE, "no forward run yet");
+  CK(cudaSetDevice(e->device));
+  td_launch_gather_xyz(e->final_buf ? e->xm1.as<float4>() : e->xm0.as<float4>(), nullptr, e->N, d_x, (cudaStream_t)stream);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return TDIFF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- sampling loop
+namespace {
+void run_step(tdiff_engine* e, cudaStream_t st, const TdStepArgs& base) {
+  run_forward(e, st, 0);
+  TdStepArgs A = base;
+  A.xm_final = e->final_buf ? e->xm1.as<float4>() : e->xm0.as<float4>();
+  td_launch_step_epilogue(A, st);
+  e->launches += 2;
+}
+}  // namespace
+
+extern "C" int tdiff_sample(tdiff_engine* e, int num_steps, const float* d_pos_noise, const float* d_v_uniform, uint64_t seed,
+                            float* d_pos_traj, int64_t* d_v_traj, float* d_v0_traj, float* d_vt_traj, int pos_only, void* stream) {
+  if (!e || !e->bound || !e->has_ligand) return set_err(TDIFF_ESTATE, "sample needs bind_batch + set_ligand first");
+  const int T = e->cfg.num_timesteps;
+  if (num_steps < 0 || num_steps > T) return set_err(TDIFF_EINVAL, "num_steps=%d outside 0..%d", num_steps, T);
+  if ((d_pos_noise == nullptr) != (d_v_uniform == nullptr) && !pos_only)
+    return set_err(TDIFF_EINVAL, "noise tape needs both pos_noise and v_uniform (or neither for Philox)");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(e->device));
+  if (num_steps == 0) return TDIFF_OK;
+  TdStepArgs A;
+  memset(&A, 0, sizeof(A));
+  A.n_lig = e->Nl; A.n_classes = e->cfg.num_classes; A.t_start = T - 1; A.pos_only = pos_only;
+  A.step = e->step.as<int>(); A.lig_node = e->lig_node.as<int>(); A.lig_graph = e->lig_graph.as<int>();
+  A.logits = e->logits.as<float>(); A.offset = e->offset.as<float4>();
+  A.c0 = e->t_c0; A.ct = e->t_ct; A.logvar = e->t_logvar; A.la_v = e->t_la; A.l1ma_v = e->t_l1ma; A.lca_v = e->t_lca; A.l1mca_v = e->t_l1mca;
+  A.log_k = (float)log((double)e->cfg.num_classes);
+  A.pos_noise = d_pos_noise; A.v_uniform = d_v_uniform; A.seed = seed;
+  A.lig_pos = e->lig_pos.as<float4>(); A.lig_v = e->lig_v.as<int>();
+  A.pos_traj = d_pos_traj; A.v_traj = (long long*)d_v_traj; A.v0_traj = d_v0_traj; A.vt_traj = d_vt_traj;
+  CK(cudaMemsetAsync(e->step.p, 0, sizeof(int), st));
+  const bool eager = e->profiling || getenv("TDIFF_NO_GRAPH") != nullptr;
+  Prof* total = new Prof(e, st, EV_TOTAL);
+  // first step eagerly (module loading, shared-memory attributes), the rest replayed from one captured graph
+  run_step(e, st, A);
+  int done = 1;
+  if (!eager && num_steps > 2) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const long long before = e->launches;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (ce == cudaSuccess) {
+      run_step(e, st, A);
+      ce = cudaStreamEndCapture(st, &graph);
+    }
+    const long long per_step = e->launches - before;
+    e->launches = before;
+    if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      delete total;
+      return set_err(TDIFF_ECUDA, "CUDA graph capture of the sampling step failed: %s", cudaGetErrorString(ce));
+    }
+    for (; done < num_steps; ++done) {
+      ce = cudaGraphLaunch(exec, st);
+      if (ce != cudaSuccess) break;
+      e->launches += per_step;
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { delete total; return set_err(TDIFF_ECUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(ce)); }
+  }
+  for (; done < num_steps; ++done) run_step(e, st, A);
+  delete total;
+  CK(cudaGetLastError());
+  return TDIFF_OK;
+}
+
+extern "C" int tdiff_sample_host(tdiff_engine* e, int B, const int32_t* pc, const int32_t* lc, const float* h_ppos, const float* h_pfeat,
+                                 const float* h_lpos, const int64_t* h_lv, int center_mode, int num_steps, const float* h_pos_noise,
+                                 const float* h_v_uniform, uint64_t seed, float* h_out_pos, int64_t* h_out_v, float* h_pos_traj,
+                                 int64_t* h_v_traj, float* h_v0_traj, float* h_vt_traj, int pos_only, void* stream) {
+  if (!e || !pc || !lc || B < 1) return set_err(TDIFF_EINVAL, "sample_host: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(e->device));
+  size_t Np = 0, Nl = 0;
+  for (int g = 0; g < B; ++g) { Np += pc[g] > 0 ? pc[g] : 0; Nl += lc[g] > 0 ? lc[g] : 0; }
+  const int F = e->cfg.protein_feat_dim, KC = e->cfg.num_classes;
+  const size_t S = num_steps > 0 ? num_steps : 0;
+  DevBuf* sb = e->stage;
+  int bad = sb[0].ensure(Np * 12 + 16) | sb[1].ensure(Np * F * 4 + 16) | sb[2].ensure(Nl * 12 + 16) | sb[3].ensure(Nl * 8 + 16);
+  if (h_pos_noise) bad |= sb[4].ensure(S * Nl * 12 + 16);
+  if (h_v_uniform) bad |= sb[5].ensure(S * Nl * KC * 4 + 16);
+  // trajectories share one staging block: pos [S,Nl,3] f32 | v [S,Nl] i64 | v0 [S,Nl,K] | vt [S,Nl,K]
+  const size_t o_pos = 0, o_v = o_pos + (h_pos_traj ? S * Nl * 12 : 0), o_v0 = (o_v + (h_v_traj ? S * Nl * 8 : 0) + 15) / 16 * 16,
+               o_vt = o_v0 + (h_v0_traj ? S * Nl * KC * 4 : 0), o_end = o_vt + (h_vt_traj ? S * Nl * KC * 4 : 0);
+  bad |= sb[6].ensure(o_end + 16) | sb[7].ensure(Nl * 12 + Nl * 8 + 32);
+  if (bad) return set_err(TDIFF_ECUDA, "out of device memory staging host buffers");
+  if (Np) {
+    CK(cudaMemcpyAsync(sb[0].p, h_ppos, Np * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sb[1].p, h_pfeat, Np * F * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (Nl) {
+    CK(cudaMemcpyAsync(sb[2].p, h_lpos, Nl * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sb[3].p, h_lv, Nl * 8, cudaMemcpyHostToDevice, st));
+  }
+  if (h_pos_noise && S * Nl) CK(cudaMemcpyAsync(sb[4].p, h_pos_noise, S * Nl * 12, cudaMemcpyHostToDevice, st));
+  if (h_v_uniform && S * Nl) CK(cudaMemcpyAsync(sb[5].p, h_v_uniform, S * Nl * KC * 4, cudaMemcpyHostToDevice, st));
+  int rc = tdiff_bind_batch(e, B, pc, lc, sb[0].as<float>(), sb[1].as<float>(), center_mode, st);
+  if (rc) return rc;
+  rc = tdiff_set_ligand(e, sb[2].as<float>(), sb[3].as<int64_t>(), center_mode == 1, st);
+  if (rc) return rc;
+  char* tb = sb[6].as<char>();
+  rc = tdiff_sample(e, num_steps, h_pos_noise ? sb[4].as<float>() : nullptr, h_v_uniform ? sb[5].as<float>() : nullptr, seed,
+                    h_pos_traj ? (float*)(tb + o_pos) : nullptr, h_v_traj ? (int64_t*)(tb + o_v) : nullptr,
+                    h_v0_traj ? (float*)(tb + o_v0) : nullptr, h_vt_traj ? (float*)(tb + o_vt) : nullptr, pos_only, st);
+  if (rc) return rc;
+  float* d_opos = sb[7].as<float>();
+  int64_t* d_ov = (int64_t*)(sb[7].as<char>() + (Nl * 12 + 15) / 16 * 16);
+  rc = tdiff_get_ligand(e, d_opos, d_ov, 1, st);
+  if (rc) return rc;
+  if (Nl) {
+    if (h_out_pos) CK(cudaMemcpyAsync(h_out_pos, d_opos, Nl * 12, cudaMemcpyDeviceToHost, st));
+    if (h_out_v) CK(cudaMemcpyAsync(h_out_v, d_ov, Nl * 8, cudaMemcpyDeviceToHost, st));
+    if (S) {
+      if (h_pos_traj) CK(cudaMemcpyAsync(h_pos_traj, tb + o_pos, S * Nl * 12, cudaMemcpyDeviceToHost, st));
+      if (h_v_traj) CK(cudaMemcpyAsync(h_v_traj, tb + o_v, S * Nl * 8, cudaMemcpyDeviceToHost, st));
+      if (h_v0_traj) CK(cudaMemcpyAsync(h_v0_traj, tb + o_v0, S * Nl * KC * 4, cudaMemcpyDeviceToHost, st));
+      if (h_vt_traj) CK(cudaMemcpyAsync(h_vt_traj, tb + o_vt, S * Nl * KC * 4, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CK(cudaStreamSynchronize(st));
+  return TDIFF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- stand-alone operators
+extern "C" int tdiff_knn_graph(const float* d_x, int n_nodes, const int32_t* h_counts, int n_graphs, int k, int32_t* d_src_slots,
+                               int64_t* d_edge_index, int64_t* h_n_edges, void* stream) {
+  if (!d_x || !h_counts || !d_src_slots || n_nodes < 0 || n_graphs < 1 || k < 1 || k > TD_KMAX) return set_err(TDIFF_EINVAL, "knn_graph: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int> ptr(n_graphs + 1, 0);
+  int max_ng = 0;
+  for (int g = 0; g < n_graphs; ++g) {
+    if (h_counts[g] < 0) return set_err(TDIFF_EINVAL, "negative count");
+    ptr[g + 1] = ptr[g] + h_counts[g];
+    if (h_counts[g] > max_ng) max_ng = h_counts[g];
+  }
+  if (ptr[n_graphs] != n_nodes) return set_err(TDIFF_EINVAL, "graph counts sum to %d, expected %d nodes", ptr[n_graphs], n_nodes);
+  if (max_ng > 2800) return set_err(TDIFF_EINVAL, "graph with %d nodes exceeds the k-NN kernel's shared-memory tile (2800)", max_ng);
+  if (n_nodes == 0) { if (h_n_edges) *h_n_edges = 0; return TDIFF_OK; }
+  DevBuf xm, dptr, off, tot;
+  int rc = TDIFF_OK;
+  if (xm.ensure((size_t)n_nodes * 16) || dptr.ensure((n_graphs + 1) * 4) || off.ensure((size_t)n_nodes * 8) || tot.ensure(8)) {
+    rc = set_err(TDIFF_ECUDA, "out of device memory");
+  } else {
+    cudaMemcpyAsync(dptr.p, ptr.data(), (n_graphs + 1) * 4, cudaMemcpyHostToDevice, st);
+    td_launch_pack_xyzm(d_x, nullptr, n_nodes, xm.as<float4>(), st);
+    td_launch_knn(xm.as<float4>(), dptr.as<int>(), n_graphs, max_ng, k, d_src_slots, st);
+    td_launch_edge_count_scan(d_src_slots, n_nodes, k, off.as<long long>(), tot.as<long long>(), st);
+    if (d_edge_index) td_launch_edge_compact(d_src_slots, nullptr, n_nodes, k, off.as<long long>(), tot.as<long long>(), (long long*)d_edge_index, nullptr, st);
+    long long t = 0;
+    cudaMemcpyAsync(&t, tot.p, 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    if (ce != cudaSuccess) rc = set_err(TDIFF_ECUDA, "knn_graph: %s", cudaGetErrorString(ce));
+    else if (h_n_edges) *h_n_edges = t;
+  }
+  xm.release(); dptr.release(); off.release(); tot.release();
+  return rc;
+}
+
+extern "C" int tdiff_attn_aggregate_h(const float* d_k, const float* d_v, const float* d_e_w, const int32_t* d_src, const float* d_q,
+                                      const float* d_h_in, float* d_h_out, int n_nodes, int kk, void* stream) {
+  if (!d_k || !d_v || !d_e_w || !d_src || !d_q || !d_h_in || !d_h_out || n_nodes < 0 || kk < 1 || kk > TD_KMAX)
+    return set_err(TDIFF_EINVAL, "attn_aggregate_h: bad arguments");
+  td_launch_aggregate_h(d_k, d_v, d_e_w, d_src, d_q, d_h_in, d_h_out, n_nodes, kk, (cudaStream_t)stream);
+  CK(cudaGetLastError());
+  return TDIFF_OK;
+}
+
+extern "C" int tdiff_attn_aggregate_x(const float* d_k, const float* d_v16, const float* d_e_w, const int32_t* d_src, const float* d_q,
+                                      const float* d_x, const uint8_t* d_mask, float* d_x_out, int n_nodes, int kk, void* stream) {
+  if (!d_k || !d_v16 || !d_e_w || !d_src || !d_q || !d_x || !d_mask || !d_x_out || n_nodes < 0 || kk < 1 || kk > TD_KMAX)
+    return set_err(TDIFF_EINVAL, "attn_aggregate_x: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_nodes == 0) return TDIFF_OK;
+  DevBuf a, b;
+  if (a.ensure((size_t)n_nodes * 16) || b.ensure((size_t)n_nodes * 16)) { a.release(); b.release(); return set_err(TDIFF_ECUDA, "out of device memory"); }
+  td_launch_pack_xyzm(d_x, d_mask, n_nodes, a.as<float4>(), st);
+  td_launch_aggregate_x(d_k, d_v16, d_e_w, d_src, d_q, a.as<float4>(), nullptr, b.as<float4>(), n_nodes, kk, st);
+  td_launch_gather_xyz(b.as<float4>(), nullptr, n_nodes, d_x_out, st);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  a.release(); b.release();
+  if (ce != cudaSuccess) return set_err(TDIFF_ECUDA, "attn_aggregate_x: %s", cudaGetErrorString(ce));
+  return TDIFF_OK;
+}
+
+extern "C" int tdiff_scatter_mean3(const float* d_src, const int32_t* h_counts, int n_segments, float* d_out, void* stream) {
+  if (!d_src || !h_counts || !d_out || n_segments < 1) return set_err(TDIFF_EINVAL, "scatter_mean3: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int> ptr(n_segments + 1, 0);
+  for (int g = 0; g < n_segments; ++g) ptr[g + 1] = ptr[g] + (h_counts[g] > 0 ? h_counts[g] : 0);
+  DevBuf dptr, o4;
+  if (dptr.ensure((n_segments + 1) * 4) || o4.ensure((size_t)n_segments * 16)) { dptr.release(); o4.release(); return set_err(TDIFF_ECUDA, "out of device memory"); }
+  cudaMemcpyAsync(dptr.p, ptr.data(), (n_segments + 1) * 4, cudaMemcpyHostToDevice, st);
+  td_launch_segment_mean3(d_src, dptr.as<int>(), n_segments, o4.as<float4>(), st);
+  td_launch_gather_xyz(o4.as<float4>(), nullptr, n_segments, d_out, st);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  dptr.release(); o4.release();
+  if (ce != cudaSuccess) return set_err(TDIFF_ECUDA, "scatter_mean3: %s", cudaGetErrorString(ce));
+  return TDIFF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- instrumentation
+extern "C" int64_t tdiff_launch_count(tdiff_engine* e) { return e ? e->launches : 0; }
+
+extern "C" int tdiff_profile(tdiff_engine* e, int enable) {
+  if (!e) return set_err(TDIFF_EINVAL, "null engine");
+  e->profiling = enable != 0;
+  if (enable) {
+    for (int i = 0; i < EV_KINDS; ++i) { e->ms_acc[i] = 0; e->n_acc[i] = 0; }
+  }
+  return TDIFF_OK;
+}
+
+extern "C" int tdiff_profile_read(tdiff_engine* e, double* ms_h, int64_t* n_h, double* ms_x, int64_t* n_x, double* ms_mlp, int64_t* n_mlp,
+                                  double* ms_total) {
+  if (!e) return set_err(TDIFF_EINVAL, "null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaDeviceSynchronize());
+  for (auto& ev : e->events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) { e->ms_acc[ev.kind] += ms; e->n_acc[ev.kind] += 1; }
+    cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+  }
+  e->events.clear();
+  if (ms_h) *ms_h = e->ms_acc[EV_AGG_H];
+  if (n_h) *n_h = e->n_acc[EV_AGG_H];
+  if (ms_x) *ms_x = e->ms_acc[EV_AGG_X];
+  if (n_x) *n_x = e->n_acc[EV_AGG_X];
+  if (ms_mlp) *ms_mlp = e->ms_acc[EV_EDGE_MLP];
+  if (n_mlp) *n_mlp = e->n_acc[EV_EDGE_MLP];
+  if (ms_total) *ms_total = e->ms_acc[EV_TOTAL];
+  return TDIFF_OK;
+}

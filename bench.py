@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- molecules/sec of the 1000-step denoising sampler (BASELINE.json metric) on N B200s, one process per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W            (driver contract; N>1 is launched through torchrun)
+    python bench.py --impl reference ...                      (the reference's algorithm on the host cores: CPU oracle port)
+
+What a "step" is: one pass of the hot path -- one denoising step (k-NN graph + 9 attention layers + type head +
+posterior update) over the whole in-flight batch.  Every step of the 1000-step chain costs the same (N and E = k*N do
+not change along the chain), so   molecules/sec = graphs_in_flight / (1000 * seconds_per_step).
+The timed K steps are consecutive steps of a real chain (Philox noise on the device), inputs resident in HBM.
+Workload (BASELINE.json configs[2], "synthetic CrossDocked-shape batch"): 64 distinct synthetic pockets x 10 samples =
+640 graphs of 300 protein + 20 ligand atoms per GPU, k=32, 9 layers, fp32.  Scaling is weak: every rank runs its own
+640-graph batch (pocket-sharded, no data-path collective; NCCL only broadcasts the weights once).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHAIN_STEPS = 1000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--pockets', type=int, default=64)
+    ap.add_argument('--samples', type=int, default=10)
+    ap.add_argument('--n-protein', type=int, default=300)
+    ap.add_argument('--n-ligand', type=int, default=20)
+    ap.add_argument('--knn', type=int, default=32)
+    ap.add_argument('--e2e-steps', type=int, default=10, help='denoising steps per end-to-end public-API call')
+    ap.add_argument('--profile-steps', type=int, default=3, help='eager steps timed per kernel with CUDA events for the roofline')
+    ap.add_argument('--cpu-graphs', type=int, default=4)
+    ap.add_argument('--cpu-steps', type=int, default=4)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return 'cfg3: %d synthetic pockets x %d samples = %d graphs x (%d protein + %d ligand atoms), k=%d, 9 layers' % (
+        a.pockets, a.samples, a.pockets * a.samples, a.n_protein, a.n_ligand, a.knn)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_rate(a, graphs, steps, warmup=1):
+    """The reference's algorithm on the host cores (oracle/restate.py, torch CPU, all threads) on a bounded sample of the
+    same workload: `graphs` graphs of the same shape x `steps` denoising steps.  Returns (molecules/s, info)."""
+    import torch
+    from oracle import restate, synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.make_state_dict(0, {'knn': a.knn}, schedules=restate.make_schedules())
+    b = synth.make_batch(1, graphs, n_protein=a.n_protein, n_ligand=a.n_ligand, distinct_pockets=graphs)
+    S = warmup + steps
+    pn, vu = synth.make_tape(7, S, len(b['batch_ligand']))
+    marks = []
+    restate.sample_diffusion(sd, {'knn': a.knn}, b['protein_pos'], b['protein_v'], b['batch_protein'], b['init_ligand_pos'],
+                             b['init_ligand_v'], b['batch_ligand'], pn, vu, num_steps=S,
+                             step_callback=lambda s, i, *r: marks.append(time.perf_counter()))
+    per_step = (marks[-1] - marks[warmup - 1]) / steps if warmup >= 1 else (marks[-1] - marks[0]) / max(1, steps - 1)
+    rate = graphs / (CHAIN_STEPS * per_step)
+    info = {'value': rate, 'unit': 'molecules/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d graphs (%d+%d atoms) x %d denoising steps after %d warm-up, %.3f s/step, extrapolated x%d steps' % (
+                graphs, a.n_protein, a.n_ligand, steps, warmup, per_step, CHAIN_STEPS)}
+    return rate, per_step, info
+
+
+def run_reference_arm(a, rank, world):
+    if rank != 0:
+        return
+    graphs = max(1, a.cpu_graphs)
+    steps = max(1, a.steps)
+    rate, per_step, info = cpu_oracle_rate(a, graphs, steps, warmup=max(1, a.warmup))
+    line = {'impl': 'reference', 'metric': 'molecules/sec (1000-step sampling, CrossDocked pocket shape)', 'value': rate, 'unit': 'molecules/s',
+            'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(a), 'chain_steps': CHAIN_STEPS,
+                       'note': 'reference algorithm (oracle port of the PyG path, torch CPU) on the host cores; bounded sample'},
+            'cpu_baseline': info, 'e2e': {'value': rate, 'unit': 'molecules/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def main():
+    a = parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if a.impl == 'reference':
+        run_reference_arm(a, rank, world)
+        return
+
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from targetdiff_b200 import _lib
+    from targetdiff_b200.config import default_model_config
+    from targetdiff_b200.score_model import ScorePosNet3D
+    from oracle import synth            # synthetic inputs only (seeded pockets / weights); not on the measured path
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    # ---- model: rank 0 builds the seeded weights, NCCL broadcast over NVLink to the other ranks (the only collective)
+    cfg = default_model_config()
+    cfg.knn = a.knn
+    model = ScorePosNet3D(cfg, synth.PROTEIN_FEATURE_DIM, synth.LIGAND_NUM_CLASSES)
+    if rank == 0:
+        sd = synth.make_state_dict(0, {'knn': a.knn}, schedules={k: getattr(model, k).data for k in synth.SCHEDULE_KEYS})
+        model.load_state_dict(sd, strict=True)
+    model = model.to(dev)
+    if world > 1:
+        flat = torch.cat([p.data.view(-1) for p in model.state_dict().values()])
+        dist.broadcast(flat, 0)
+        off = 0
+        for p in model.state_dict().values():
+            p.data.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        model._drop_engine()
+
+    # ---- synthetic batch of this rank (different pockets per rank), staged in pinned host memory
+    G = a.pockets * a.samples
+    b = synth.make_batch(100 + rank, G, n_protein=a.n_protein, n_ligand=a.n_ligand, distinct_pockets=a.pockets)
+    host = {k: v.pin_memory() for k, v in b.items()}
+    N = G * (a.n_protein + a.n_ligand)
+    E = N * a.knn
+    Nl = G * a.n_ligand
+    K = synth.LIGAND_NUM_CLASSES
+
+    def to_dev():
+        return {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+
+    d = to_dev()
+    args = (d['protein_pos'], d['protein_v'], d['batch_protein'], d['init_ligand_pos'], d['init_ligand_v'], d['batch_ligand'])
+    eng = model.engine(dev)
+    st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    model._bind(eng, d['protein_pos'], d['protein_v'], d['batch_protein'], d['batch_ligand'], 1)
+    _lib.check(lib.tdiff_set_ligand(eng, ctypes.c_void_p(d['init_ligand_pos'].data_ptr()), ctypes.c_void_p(d['init_ligand_v'].data_ptr()), 1, st))
+
+    def chain(steps, seed):
+        _lib.check(lib.tdiff_sample(eng, steps, None, None, ctypes.c_uint64(seed), None, None, None, None, 0, st))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up, then EXACTLY K timed denoising steps (device events, max over ranks)
+    chain(max(3, a.warmup), 1)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = lib.tdiff_launch_count(eng)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(torch.cuda.current_stream(dev))
+    chain(a.steps, 2)
+    ev1.record(torch.cuda.current_stream(dev))
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.tdiff_launch_count(eng) - l0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / a.steps
+    value = world * G / (CHAIN_STEPS * ms_per_step * 1e-3)
+
+    # ---- per-kernel timing (eager launches bracketed by CUDA events on the launch stream) for the roofline
+    roofline, extra = None, {}
+    if rank == 0 and a.profile_steps > 0:
+        _lib.check(lib.tdiff_profile(eng, 1))
+        chain(a.profile_steps, 3)
+        vals = [ctypes.c_double() for _ in range(4)]
+        cnts = [ctypes.c_int64() for _ in range(3)]
+        _lib.check(lib.tdiff_profile_read(eng, ctypes.byref(vals[0]), ctypes.byref(cnts[0]), ctypes.byref(vals[1]), ctypes.byref(cnts[1]),
+                                          ctypes.byref(vals[2]), ctypes.byref(cnts[2]), ctypes.byref(vals[3])))
+        _lib.check(lib.tdiff_profile(eng, 0))
+        peak, peak_src = measured_peaks()
+        ms_h, n_h = vals[0].value, cnts[0].value
+        ms_x, n_x = vals[1].value, cnts[1].value
+        ms_mlp, n_mlp = vals[2].value, cnts[2].value
+        tot = vals[3].value
+        if n_h:
+            t_h = ms_h / n_h * 1e-3
+            bytes_h = E * 1028 + N * 1536                           # k 512 + v 512 + e_w 4 per edge; q, h, out per node
+            ach = bytes_h / t_h / 1e9
+            roofline = {'kernel': 'aggregate_h_kernel (fused scatter_softmax->scatter_sum, x2h)', 'bound': 'hbm', 'achieved': ach,
+                        'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                        'algorithmic_bytes_per_launch': bytes_h, 'avg_launch_ms': t_h * 1e3, 'launches_timed': n_h,
+                        'share_of_step': ms_h / tot if tot else None}
+        if n_x:
+            El = Nl * a.knn
+            bytes_x = El * 596 + Nl * 537
+            t_x = ms_x / n_x * 1e-3
+            extra['roofline_aggregate_x'] = {'kernel': 'aggregate_x_kernel (h2x, ligand destinations only)', 'bound': 'hbm',
+                                             'achieved': bytes_x / t_x / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': bytes_x / t_x / 1e9 / peak,
+                                             'avg_launch_ms': t_x * 1e3, 'share_of_step': ms_x / tot if tot else None}
+        if n_mlp:
+            # executed flops of the FFMA edge-MLP path: per x2h edge 2 MLPs x (128*128 + 20*128) MAC; per ligand-dst edge (h2x)
+            # (128*128 + 20*128) + (128*16 + 20*128) MAC
+            flops = 2.0 * (E * 2 * (128 * 128 + 20 * 128) + Nl * a.knn * ((128 * 128 + 20 * 128) + (128 * 16 + 20 * 128)))
+            t_m = ms_mlp / (n_mlp / 2) * 1e-3                       # per layer (x2h pair + h2x pair)
+            extra['edge_mlp'] = {'kernel': 'edge_mlp_kernel (FP32 FFMA)', 'executed_tflops': flops / t_m / 1e12,
+                                 'ms_per_layer': t_m * 1e3, 'share_of_step': ms_mlp / tot if tot else None}
+        extra['profile_ms_per_step_eager'] = tot / a.profile_steps if tot else None
+
+    # ---- end to end through the public API with HOST buffers (H2D of the inputs, the chain, D2H of results + trajectories)
+    e2e = None
+    if not a.no_e2e:
+        S = max(3, a.e2e_steps)
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = Nl * 12 + Nl * 8 + S * Nl * (12 + 8 + 2 * K * 4)
+        reps = 2
+
+        def one_call(seed):
+            dd = to_dev()
+            r = model.sample_diffusion(dd['protein_pos'], dd['protein_v'], dd['batch_protein'], dd['init_ligand_pos'], dd['init_ligand_v'],
+                                       dd['batch_ligand'], num_steps=S, center_pos_mode='protein', seed=seed, stack_traj=True)
+            return r['pos'].cpu(), r['v'].cpu()
+
+        one_call(11)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(reps):
+            one_call(12 + i)
+        torch.cuda.synchronize(dev)
+        t_call = (time.perf_counter() - t0) / reps
+        if world > 1:
+            t = torch.tensor([t_call], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_call = float(t.item())
+        e2e = {'value': world * G / (CHAIN_STEPS * (t_call / S)), 'unit': 'molecules/s', 'h2d_bytes_per_step': h2d / S,
+               'd2h_bytes_per_step': d2h / S,
+               'note': 'ScorePosNet3D.sample_diffusion(num_steps=%d) per call from pinned host tensors incl. batch binding, H2D, chain, '
+                       'D2H of final state and all four trajectories; per-step cost x1000 (a real 1000-step call amortises the copies '
+                       '%dx better)' % (S, CHAIN_STEPS // S)}
+
+    # ---- CPU baseline (rank 0, N=1 only; bounded sample)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        _, _, cpu = cpu_oracle_rate(a, a.cpu_graphs, a.cpu_steps)
+
+    if rank == 0:
+        line = {'metric': 'molecules/sec (1000-step sampling, CrossDocked pocket shape)', 'value': value, 'unit': 'molecules/s', 'n_gpus': world,
+                'steps': a.steps, 'warmup': max(3, a.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': workload_name(a), 'graphs_per_gpu': G, 'nodes': N, 'edges': E, 'chain_steps': CHAIN_STEPS,
+                           'step': 'one denoising step of the whole in-flight batch; value = graphs / (1000 * s_per_step)',
+                           'parallelism': 'pocket-sharded x%d (no data-path collective)' % world,
+                           'l2': 'per-step working set (k,v edge tensors %.1f GB) >> 126 MB L2; no explicit flush' % (2 * E * 512 / 1e9),
+                           'noise': 'device Philox4x32-10'},
+                'clocks': clocks, 'gpu_launches': int(launches), 'e2e': e2e, 'roofline': roofline, 'cpu_baseline': cpu}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -75,6 +75,8 @@ struct tdiff_engine {
   DevBuf step, err_flag, node_off, total_edges;
   DevBuf stage[8];   // staging for tdiff_sample_host
   // ---- instrumentation
+  cudaStream_t own_stream = nullptr;   // capture stream (the caller's stream may be the legacy default stream, which cannot capture)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   long long launches = 0;
   bool profiling = false;
   std::vector<EvPair> events;
@@ -303,6 +305,11 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     tdiff_destroy(e); return set_err(TDIFF_ECUDA, "cudaMalloc failed");
   }
   cudaMemset(e->err_flag.p, 0, sizeof(int));
+  if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    tdiff_destroy(e); return set_err(TDIFF_ECUDA, "stream/event creation failed");
+  }
   *out = e;
   return TDIFF_OK;
 }
@@ -311,6 +318,9 @@ extern "C" void tdiff_destroy(tdiff_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   for (auto& ev : e->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   DevBuf* bufs[] = {&e->node_ptr, &e->prot_ptr, &e->prot_node, &e->prot_graph, &e->lig_node, &e->lig_graph, &e->node_lig, &e->xm0, &e->xm1,
                     &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->etype, &e->e_w, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
                     &e->lig_v, &e->logits, &e->step, &e->err_flag, &e->node_off, &e->total_edges};
@@ -593,28 +603,35 @@ extern "C" int tdiff_sample(tdiff_engine* e, int num_steps, const float* d_pos_n
   run_step(e, st, A);
   int done = 1;
   if (!eager && num_steps > 2) {
+    // fork onto the engine's own stream: capture there (the caller's stream may be the legacy default stream), replay, join back
+    cudaStream_t cs = e->own_stream;
+    CK(cudaEventRecord(e->ev_fork, st));
+    CK(cudaStreamWaitEvent(cs, e->ev_fork, 0));
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     const long long before = e->launches;
-    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
     if (ce == cudaSuccess) {
-      run_step(e, st, A);
-      ce = cudaStreamEndCapture(st, &graph);
+      run_step(e, cs, A);
+      ce = cudaStreamEndCapture(cs, &graph);
     }
     const long long per_step = e->launches - before;
     e->launches = before;
     if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
     if (ce != cudaSuccess) {
       if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
       delete total;
       return set_err(TDIFF_ECUDA, "CUDA graph capture of the sampling step failed: %s", cudaGetErrorString(ce));
     }
     for (; done < num_steps; ++done) {
-      ce = cudaGraphLaunch(exec, st);
+      ce = cudaGraphLaunch(exec, cs);
       if (ce != cudaSuccess) break;
       e->launches += per_step;
     }
-    cudaGraphExecDestroy(exec);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e->ev_join, cs);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(st, e->ev_join, 0);
+    cudaGraphExecDestroy(exec);      // deferred by the runtime until the launched replays have finished
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { delete total; return set_err(TDIFF_ECUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(ce)); }
   }

@@ -299,13 +299,15 @@ class ScorePosNet3D(nn.Module):
 
     @torch.no_grad()
     def sample_diffusion(self, protein_pos, protein_v, batch_protein, init_ligand_pos, init_ligand_v, batch_ligand,
-                         num_steps=None, center_pos_mode=None, pos_only=False, noise_tape=None, seed=None, return_traj=True):
+                         num_steps=None, center_pos_mode=None, pos_only=False, noise_tape=None, seed=None, return_traj=True,
+                         stack_traj=False):
         """The reverse-diffusion chain (reference models/molopt_score_model.py:633-703), executed entirely by libtdiff.so.
 
         Extensions over the reference signature (all optional): `noise_tape=(pos_noise [S,Nl,3], v_uniform [S,Nl,K])`
         replaces the RNG in the reference's draw order (parity tests); `seed` keys the device Philox generator (default:
         drawn from torch's global CPU generator, so `seed_all` makes runs reproducible); `return_traj=False` skips the
-        four trajectory outputs."""
+        four trajectory outputs; `stack_traj=True` returns each trajectory as one stacked CPU tensor [S, ...] instead
+        of the reference's list of per-step tensors."""
         if num_steps is None:
             num_steps = self.num_timesteps
         mode = {None: 0, 'none': 0, 'protein': 1}.get(center_pos_mode, None)
@@ -340,7 +342,10 @@ class ScorePosNet3D(nn.Module):
         out_pos = torch.empty(Nl, 3, device=dev)
         out_v = torch.empty(Nl, dtype=torch.int64, device=dev)
         _lib.check(lib.tdiff_get_ligand(eng, _ptr(out_pos), _ptr(out_v), 1, st))
-        as_list = lambda t: list(t.cpu().unbind(0)) if t is not None else []      # one D2H per trajectory, not one per step
+        if stack_traj:
+            as_list = lambda t: t.cpu() if t is not None else None
+        else:
+            as_list = lambda t: list(t.cpu().unbind(0)) if t is not None else []  # one D2H per trajectory, not one per step
         return {'pos': out_pos, 'v': out_v, 'pos_traj': as_list(pos_traj), 'v_traj': as_list(v_traj), 'v0_traj': as_list(v0_traj),
                 'vt_traj': as_list(vt_traj)}
 

@@ -1,0 +1,370 @@
+// edge_mlp_tc.cu -- per-edge MLPs with the second Linear on the 5th-gen tensor cores (tcgen05 + TMEM), fp32-faithful.
+//
+// Same math as edge_mlp.cu (reference models/uni_transformer.py:45-56,111-120 + models/common.py:60-80 after the exact
+// first-layer split of SURVEY.md Appendix B); different execution:
+//
+//   * the [128 edges x 128] hidden tile and the [128 x 128] weight are split into NP bf16 pieces each
+//     (x = x1 + x2 (+ x3), xi = bf16(residual)); the product is recovered with 3 (NP=2) or 6 (NP=3) tcgen05.mma
+//     kind::f16 passes accumulating in fp32 in TMEM:  a1b1 + a1b2 + a2b1 (+ a1b3 + a2b2 + a3b1).
+//     NP=3 keeps 24 mantissa bits of both operands (error ~2^-22, i.e. fp32 GEMM class); NP=2 keeps 16.
+//     Plain TF32 / BF16 single-pass MMA would break the 1e-4 position tolerance.
+//   * warp-specialised persistent CTA (one per SM), 13 warps:
+//       warps 0-3   epilogue: tcgen05.ld accumulator rows (warp q owns TMEM lanes 32q..32q+31) -> +bias -> global
+//       warp  4     TMEM allocator + single-thread MMA issuer (tcgen05.mma / tcgen05.commit)
+//       warps 5-12  producers: 8 edge rows per warp in registers -- coalesced 512 B gathers of the projected node
+//                   rows, gaussians by 4 lanes per row, type/gaussian table through L1 (one table row feeds 8 edge rows),
+//                   LayerNorm by shuffles, ReLU, bf16 split, 8-byte stores into the UMMA K-major SWIZZLE_128B layout
+//     mbarriers: a_full/a_empty (producers <-> MMA), d_full/d_empty (MMA <-> epilogue, accumulator double-buffered in TMEM).
+//   * the weight pieces are pre-swizzled on the host into the exact shared-memory image (engine.cu: pack_umma_image).
+//
+// Shared memory: NP*32 KB weights + NBUF*NP*32 KB activation tiles (+2 KB) -> 194 KB for (NP=3,NBUF=1) and (NP=2,NBUF=2).
+#include "tdiff_common.cuh"
+
+namespace {
+
+constexpr int kEpiWarps = 4;
+constexpr int kMmaWarp = 4;
+constexpr int kProdWarp0 = 5;
+constexpr int kProdWarps = 8;
+constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;   // 416
+constexpr int kPieceBytes = 128 * 128 * 2;                 // one bf16 piece of a 128x128 tile
+constexpr int kAtomBytes = 128 * 128;                      // 128 rows x 64 bf16 (128 B) : one K-half
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T ; bf16 inputs, fp32 accumulate, M=128, N=128, K=16 per instruction
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor fields:
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64))
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// two fp32 -> packed bf16x2 (round-to-nearest-even): `lo` in bits [0,16), `hi` in bits [16,32)
+__device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+template <int NP>
+__device__ __forceinline__ void split_store_row(unsigned char* a_tile, int row, int lane, const float (&y)[4]) {
+  // features 4*lane .. 4*lane+3 of `row` -> NP pieces; byte offset inside a piece (K-major SWIZZLE_128B, two K-halves)
+  const int khalf = lane >> 4, chunk = (lane & 15) >> 1;
+  const uint32_t off = khalf * kAtomBytes + row * 128 + ((chunk ^ (row & 7)) << 4) + ((lane & 1) << 3);
+  float r[4] = {y[0], y[1], y[2], y[3]};
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const uint2 v = make_uint2(cvt_bf16x2(r[1], r[0]), cvt_bf16x2(r[3], r[2]));
+    r[0] -= __uint_as_float(v.x << 16); r[1] -= __uint_as_float(v.x & 0xffff0000u);       // residuals are exact in fp32
+    r[2] -= __uint_as_float(v.y << 16); r[3] -= __uint_as_float(v.y & 0xffff0000u);
+    *reinterpret_cast<uint2*>(a_tile + p * kPieceBytes + off) = v;
+  }
+}
+
+}  // namespace
+
+template <int NP, int NBUF>
+__global__ void __launch_bounds__(kThreads, 1)
+edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, const int* __restrict__ src,
+                   const unsigned char* __restrict__ etype, const int* __restrict__ row_nodes, long long n_rows, int k, TdMlp m,
+                   const unsigned char* __restrict__ w2_image, const float* __restrict__ offsets, float coeff, float* __restrict__ out) {
+  extern __shared__ unsigned char smem_raw[];
+  // carve (1024-byte aligned: SWIZZLE_128B atoms)
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sB = base;                                   // NP pieces
+  unsigned char* sA = sB + NP * kPieceBytes;                  // NBUF x NP pieces
+  float* s_b2 = reinterpret_cast<float*>(sA + NBUF * NP * kPieceBytes);   // [128]
+  float* s_g = s_b2 + TD_H;
+  float* s_b = s_g + TD_H;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + TD_H);  // a_full[NBUF], a_empty[NBUF], d_full[2], d_empty[2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * NBUF + 4);
+  const uint32_t bar_a_full = smem_u32(bars), bar_a_empty = smem_u32(bars + NBUF), bar_d_full = smem_u32(bars + 2 * NBUF),
+                 bar_d_empty = smem_u32(bars + 2 * NBUF + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- one-time setup: weights image -> smem, params, barriers, TMEM
+  for (int i = tid; i < NP * kPieceBytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(w2_image)[i];
+  for (int i = tid; i < TD_H; i += kThreads) { s_b2[i] = m.b2[i]; s_g[i] = m.ln_g[i]; s_b[i] = m.ln_b[i]; }
+  if (tid == 0) {
+    for (int i = 0; i < NBUF; ++i) {
+      mbar_init(bar_a_full + 8 * i, kProdWarps);
+      mbar_init(bar_a_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_d_full + 8 * i, 1);
+      mbar_init(bar_d_empty + 8 * i, kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(s_tmem), 256);
+  fence_proxy_async();            // weight image (generic-proxy stores) -> visible to the tensor-core (async) proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const long long n_tiles = (n_rows + 127) / 128;
+  const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp >= kProdWarp0) {
+    // =============================================================== producers
+    const int pw = warp - kProdWarp0;            // 0..7, owns rows pw*16 .. pw*16+15 of the tile (two groups of 8)
+    const int rsub = lane >> 2, jq = lane & 3;   // metadata: lane handles row `rsub` of the group, gaussians 5*jq .. 5*jq+4
+    float mu[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) mu[i] = offsets[5 * jq + i];
+    for (long long it = 0; it < my_tiles; ++it) {
+      const long long tile = blockIdx.x + it * gridDim.x;
+      const int buf = (int)(it % NBUF);
+      const uint32_t ph = (uint32_t)((it / NBUF) & 1);
+      mbar_wait(bar_a_empty + 8 * buf, ph ^ 1);          // first use of a buffer passes immediately
+      unsigned char* a_tile = sA + buf * NP * kPieceBytes;
+#pragma unroll 1
+      for (int grp = 0; grp < 2; ++grp) {
+        const int r0 = pw * 16 + grp * 8;
+        // ---- per-row metadata, 4 lanes per row
+        const long long idx = tile * 128 + r0 + rsub;
+        int s = -1, dst = 0, ty = 0;
+        float g[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (idx < n_rows) {
+          const long long a = idx / k;
+          const int j = (int)(idx - a * k);
+          dst = row_nodes ? row_nodes[a] : (int)a;
+          const long long e = (long long)dst * k + j;
+          s = src[e];
+          if (s >= 0) {
+            ty = etype[e];
+            const float4 xd = xm[dst], xs = xm[s];
+            const float dx = xd.x - xs.x, dy = xd.y - xs.y, dz = xd.z - xs.z;
+            const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              const float t = dist - mu[i];
+              g[i] = expf(coeff * (t * t));
+            }
+          }
+        }
+        // ---- gathers: acc[r] = P[dst_r, offA + 4l..] + P[src_r, offB + 4l..]   (512 B coalesced per row)
+        float acc[8][4];
+        int s_r[8], t_r[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          s_r[r] = __shfl_sync(0xffffffffu, s, r * 4);
+          t_r[r] = __shfl_sync(0xffffffffu, ty, r * 4);
+          const int d_r = __shfl_sync(0xffffffffu, dst, r * 4);
+          if (s_r[r] >= 0) {
+            const float4 pa = *reinterpret_cast<const float4*>(P + (size_t)d_r * TD_NPROJ + m.offA + 4 * lane);
+            const float4 pb = *reinterpret_cast<const float4*>(P + (size_t)s_r[r] * TD_NPROJ + m.offB + 4 * lane);
+            acc[r][0] = pa.x + pb.x; acc[r][1] = pa.y + pb.y; acc[r][2] = pa.z + pb.z; acc[r][3] = pa.w + pb.w;
+          } else {
+            acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+          }
+        }
+        // ---- type / gaussian block of the first Linear: one table row (L1) feeds the 8 edge rows of the group
+        unsigned present = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) present |= (s_r[r] >= 0) ? (1u << t_r[r]) : 0u;
+#pragma unroll 1
+        for (int t = 0; t < 4; ++t) {
+          if (!((present >> t) & 1u)) continue;
+          const float* tb = m.tab + (size_t)t * TD_TAB * TD_H + 4 * lane;
+          const bool mine = (s >= 0) && (ty == t);
+          {
+            const float4 c = __ldg(reinterpret_cast<const float4*>(tb + TD_NG * TD_H));     // type column + bias
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const float w = (s_r[r] >= 0 && t_r[r] == t) ? 1.0f : 0.0f;
+              acc[r][0] = fmaf(w, c.x, acc[r][0]); acc[r][1] = fmaf(w, c.y, acc[r][1]);
+              acc[r][2] = fmaf(w, c.z, acc[r][2]); acc[r][3] = fmaf(w, c.w, acc[r][3]);
+            }
+          }
+#pragma unroll
+          for (int jj = 0; jj < TD_NG; ++jj) {
+            const float4 c = __ldg(reinterpret_cast<const float4*>(tb + jj * TD_H));
+            const float gm = mine ? g[jj % 5] : 0.0f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const float w = __shfl_sync(0xffffffffu, gm, r * 4 + jj / 5);
+              acc[r][0] = fmaf(w, c.x, acc[r][0]); acc[r][1] = fmaf(w, c.y, acc[r][1]);
+              acc[r][2] = fmaf(w, c.z, acc[r][2]); acc[r][3] = fmaf(w, c.w, acc[r][3]);
+            }
+          }
+        }
+        // ---- LayerNorm + ReLU + bf16 split + swizzled store
+        const float4 g4 = *reinterpret_cast<const float4*>(s_g + 4 * lane);
+        const float4 b4 = *reinterpret_cast<const float4*>(s_b + 4 * lane);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          float y[4] = {0.f, 0.f, 0.f, 0.f};
+          if (s_r[r] >= 0) {
+            const float mean = warp_sum((acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3])) * (1.0f / 128.0f);
+            const float d0 = acc[r][0] - mean, d1 = acc[r][1] - mean, d2 = acc[r][2] - mean, d3 = acc[r][3] - mean;
+            const float var = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) * (1.0f / 128.0f);
+            const float rstd = 1.0f / sqrtf(var + 1e-5f);
+            y[0] = fmaxf(d0 * rstd * g4.x + b4.x, 0.f);
+            y[1] = fmaxf(d1 * rstd * g4.y + b4.y, 0.f);
+            y[2] = fmaxf(d2 * rstd * g4.z + b4.z, 0.f);
+            y[3] = fmaxf(d3 * rstd * g4.w + b4.w, 0.f);
+          }
+          split_store_row<NP>(a_tile, r0 + r, lane, y);
+        }
+      }
+      fence_proxy_async();          // activation tile -> visible to the tensor-core proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a_full + 8 * buf);
+    }
+  } else if (warp == kMmaWarp) {
+    // =============================================================== MMA issuer (one thread)
+    for (long long it = 0; it < my_tiles; ++it) {
+      const int buf = (int)(it % NBUF);
+      const uint32_t pha = (uint32_t)((it / NBUF) & 1);
+      const int db = (int)(it & 1);
+      const uint32_t phd = (uint32_t)((it >> 1) & 1);
+      mbar_wait(bar_d_empty + 8 * db, phd ^ 1);          // accumulator buffer drained by the epilogue
+      mbar_wait(bar_a_full + 8 * buf, pha);              // activation tile written
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(sA + buf * NP * kPieceBytes), b_addr = smem_u32(sB);
+        const uint32_t d_addr = tmem_base + (uint32_t)db * 128;
+        uint32_t accum = 0;
+        // terms (pa, pb) with pa + pb <= NP-1:  a1b1 | a1b2, a2b1 | a1b3, a2b2, a3b1 ; smallest contributions last
+#pragma unroll
+        for (int sum = 0; sum < NP; ++sum) {
+#pragma unroll
+          for (int pa = 0; pa <= sum; ++pa) {
+            const int pb = sum - pa;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {             // K = 128 in 8 instructions of K=16 (32 B inside a 128 B swizzle row)
+              const uint32_t koff = (kk >> 2) * kAtomBytes + (kk & 3) * 32;
+              umma_bf16(d_addr, umma_desc_k_sw128(a_addr + pa * kPieceBytes + koff), umma_desc_k_sw128(b_addr + pb * kPieceBytes + koff),
+                        kIdesc, accum);
+              accum = 1;
+            }
+          }
+        }
+        umma_commit(bar_a_empty + 8 * buf);              // activation tile may be overwritten once these MMAs retire
+        umma_commit(bar_d_full + 8 * db);                // accumulator ready for the epilogue
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================================================== epilogue (warps 0..3 <-> TMEM lanes 32w..32w+31)
+    for (long long it = 0; it < my_tiles; ++it) {
+      const long long tile = blockIdx.x + it * gridDim.x;
+      const int db = (int)(it & 1);
+      const uint32_t phd = (uint32_t)((it >> 1) & 1);
+      mbar_wait(bar_d_full + 8 * db, phd);
+      tc_fence_after();
+      const long long idx = tile * 128 + warp * 32 + lane;
+      float* orow = out + (size_t)idx * 128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(db * 128 + c0), v);
+        if (idx < n_rows) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            const float4 bia = *reinterpret_cast<const float4*>(s_b2 + c0 + c);
+            float4 o;
+            o.x = __uint_as_float(v[c]) + bia.x; o.y = __uint_as_float(v[c + 1]) + bia.y;
+            o.z = __uint_as_float(v[c + 2]) + bia.z; o.w = __uint_as_float(v[c + 3]) + bia.w;
+            *reinterpret_cast<float4*>(orow + c0 + c) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_d_empty + 8 * db);
+    }
+  }
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+template <int NP, int NBUF>
+static void launch_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes, long long n_rows,
+                      int k, TdMlp m, const unsigned char* w2_image, const float* offsets, float coeff, float* out, int sm_count,
+                      cudaStream_t st) {
+  const size_t smem = 1024 + (size_t)NP * kPieceBytes + (size_t)NBUF * NP * kPieceBytes + 3 * TD_H * sizeof(float) + (2 * NBUF + 4) * 8 + 16;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(edge_mlp_tc_kernel<NP, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  const long long n_tiles = (n_rows + 127) / 128;
+  const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
+  edge_mlp_tc_kernel<NP, NBUF><<<grid, kThreads, smem, st>>>(P, xm, src, etype, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out);
+}
+
+// pieces = 3: 6-term product (fp32-class accuracy); pieces = 2: 3-term product (16 mantissa bits).  nout must be 128.
+void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
+                           long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
+                           float* out, int sm_count, cudaStream_t st) {
+  if (n_rows == 0) return;
+  if (pieces == 2) launch_tc<2, 2>(P, xm, src, etype, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, sm_count, st);
+  else launch_tc<3, 1>(P, xm, src, etype, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, sm_count, st);
+}

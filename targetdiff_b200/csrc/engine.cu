@@ -61,6 +61,8 @@ struct tdiff_engine {
   int device = 0, sm_count = 148;
   // ---- weights (one device arena)
   float* arena = nullptr;
+  unsigned char* img_arena = nullptr;   // bf16-split second-layer weights in the tensor-core shared-memory image
+  int mlp_mode = 3;                     // 0: FP32 FFMA (edge_mlp.cu), 2: tcgen05 3-term bf16 split, 3: tcgen05 6-term (fp32-class)
   std::vector<TdLayer> layers;
   const float *w_prot = nullptr, *b_prot = nullptr, *wl_t = nullptr, *bl = nullptr;
   const float *ew_w1t = nullptr, *ew_b1 = nullptr, *ew_g = nullptr, *ew_b = nullptr, *ew_w2 = nullptr, *ew_off = nullptr;
@@ -89,6 +91,7 @@ namespace {
 struct Packer {
   std::map<std::string, const tdiff_tensor*> byname;
   std::vector<float> host;
+  std::vector<unsigned char> img;
   std::string missing;
   const float* get(const std::string& name, int64_t numel) {
     auto it = byname.find(name);
@@ -105,7 +108,31 @@ struct Packer {
   }
 };
 
-struct MlpOff { size_t tab, ln_g, ln_b, w2t, b2; int nout; };
+struct MlpOff { size_t tab, ln_g, ln_b, w2t, b2; int nout; long long img; };
+
+// round-to-nearest-even fp32 -> bf16 bit pattern
+inline uint16_t bf16_rn(float x) {
+  uint32_t u; memcpy(&u, &x, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf16_f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+
+// W2 [128 out (N), 128 in (K)] -> three bf16 pieces (w = w1 + w2 + w3), each stored as the shared-memory image the UMMA
+// descriptor of edge_mlp_tc.cu expects: K-major, SWIZZLE_128B, two K-halves of [128 rows x 128 B], 16-byte chunks XOR row%8.
+void pack_umma_image(const float* w2, std::vector<unsigned char>& img, size_t off) {
+  for (int n = 0; n < 128; ++n)
+    for (int kk = 0; kk < 128; ++kk) {
+      float r = w2[(size_t)n * 128 + kk];
+      const size_t o = (size_t)(kk / 64) * 16384 + (size_t)n * 128 + (size_t)((((kk % 64) / 8) ^ (n & 7)) * 16) + (size_t)(kk % 8) * 2;
+      for (int p = 0; p < 3; ++p) {
+        const uint16_t b = bf16_rn(r);
+        r = r - bf16_f(b);
+        memcpy(&img[off + (size_t)p * 32768 + o], &b, 2);
+      }
+    }
+}
 
 // edge MLP: first Linear [128, 4 + 80 + 128 + 128] split, LayerNorm affine, second Linear transposed
 bool pack_edge_mlp(Packer& pk, const std::string& p, int nout, MlpOff& o, const float** w1_out) {
@@ -130,6 +157,12 @@ bool pack_edge_mlp(Packer& pk, const std::string& p, int nout, MlpOff& o, const 
   for (int kk = 0; kk < TD_H; ++kk)
     for (int n = 0; n < nout; ++n) pk.host[o.w2t + (size_t)kk * nout + n] = w2[(size_t)n * TD_H + kk];
   o.b2 = pk.alloc(nout); memcpy(&pk.host[o.b2], b2, nout * sizeof(float));
+  o.img = -1;
+  if (nout == TD_H) {
+    o.img = (long long)pk.img.size();
+    pk.img.resize(pk.img.size() + 3 * 32768, 0);
+    pack_umma_image(w2, pk.img, (size_t)o.img);
+  }
   *w1_out = w1;
   return true;
 }
@@ -149,7 +182,7 @@ bool pack_sublayer(Packer& pk, const std::string& p, const char* kn, const char*
   const float* w2q = pk.get(qp + ".net.3.weight", (int64_t)TD_H * TD_H);
   const float* b2q = pk.get(qp + ".net.3.bias", TD_H);
   if (!w1q || !b1q || !gq || !bq || !w2q || !b2q) return false;
-  so.q.nout = TD_H; so.q.tab = 0;
+  so.q.nout = TD_H; so.q.tab = 0; so.q.img = -1;
   so.q.ln_g = pk.alloc(TD_H); memcpy(&pk.host[so.q.ln_g], gq, TD_H * sizeof(float));
   so.q.ln_b = pk.alloc(TD_H); memcpy(&pk.host[so.q.ln_b], bq, TD_H * sizeof(float));
   so.q.w2t = pk.alloc((size_t)TD_H * TD_H);
@@ -172,8 +205,9 @@ bool pack_sublayer(Packer& pk, const std::string& p, const char* kn, const char*
   return true;
 }
 
-TdMlp mk_mlp(const float* base, const MlpOff& o, int offA, int offB) {
+TdMlp mk_mlp(const float* base, const unsigned char* img_base, const MlpOff& o, int offA, int offB) {
   TdMlp m;
+  m.w2_img = (o.img >= 0 && img_base) ? img_base + o.img : nullptr;
   m.tab = base + o.tab; m.ln_g = base + o.ln_g; m.ln_b = base + o.ln_b; m.w2t = base + o.w2t; m.b2 = base + o.b2;
   m.nout = o.nout; m.offA = offA; m.offB = offB;
   return m;
@@ -286,7 +320,20 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
   if (cudaMemcpy(e->arena, pk.host.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaFree(e->arena); delete e; return set_err(TDIFF_ECUDA, "weight upload failed");
   }
+  if (!pk.img.empty()) {
+    if (cudaMalloc(&e->img_arena, pk.img.size()) != cudaSuccess ||
+        cudaMemcpy(e->img_arena, pk.img.data(), pk.img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaFree(e->arena); delete e; return set_err(TDIFF_ECUDA, "weight image upload failed");
+    }
+  }
+  if (const char* mode = getenv("TDIFF_EDGE_MLP")) {
+    if (!strcmp(mode, "simt")) e->mlp_mode = 0;
+    else if (!strcmp(mode, "tc3")) e->mlp_mode = 2;
+    else if (!strcmp(mode, "tc6")) e->mlp_mode = 3;
+    else { cudaFree(e->arena); cudaFree(e->img_arena); delete e; return set_err(TDIFF_EINVAL, "TDIFF_EDGE_MLP=%s (simt|tc3|tc6)", mode); }
+  }
   const float* A = e->arena;
+  const unsigned char* IM = e->img_arena;
   e->t_c0 = A + tabs[0].off; e->t_ct = A + tabs[1].off; e->t_logvar = A + tabs[2].off; e->t_la = A + tabs[3].off;
   e->t_l1ma = A + tabs[4].off; e->t_lca = A + tabs[5].off; e->t_l1mca = A + tabs[6].off;
   e->w_prot = A + o_wp; e->b_prot = A + o_bp; e->wl_t = A + o_wl; e->bl = A + o_bl;
@@ -297,9 +344,9 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     TdLayer& ly = e->layers[l];
     ly.offsets = A + o_off[l]; ly.coeff = coeffs[l];
     ly.x2h.wn_t = A + sx[l].wn_t; ly.x2h.bn = A + sx[l].bn;
-    ly.x2h.k = mk_mlp(A, sx[l].k, 0, 256); ly.x2h.v = mk_mlp(A, sx[l].v, 128, 384); ly.x2h.q = mk_mlp(A, sx[l].q, 512, 512);
+    ly.x2h.k = mk_mlp(A, IM, sx[l].k, 0, 256); ly.x2h.v = mk_mlp(A, IM, sx[l].v, 128, 384); ly.x2h.q = mk_mlp(A, IM, sx[l].q, 512, 512);
     ly.h2x.wn_t = A + sh[l].wn_t; ly.h2x.bn = A + sh[l].bn;
-    ly.h2x.k = mk_mlp(A, sh[l].k, 0, 256); ly.h2x.v = mk_mlp(A, sh[l].v, 128, 384); ly.h2x.q = mk_mlp(A, sh[l].q, 512, 512);
+    ly.h2x.k = mk_mlp(A, IM, sh[l].k, 0, 256); ly.h2x.v = mk_mlp(A, IM, sh[l].v, 128, 384); ly.h2x.q = mk_mlp(A, IM, sh[l].q, 512, 512);
   }
   if (e->step.ensure(sizeof(int)) || e->err_flag.ensure(sizeof(int)) || e->total_edges.ensure(sizeof(long long))) {
     tdiff_destroy(e); return set_err(TDIFF_ECUDA, "cudaMalloc failed");
@@ -327,6 +374,7 @@ extern "C" void tdiff_destroy(tdiff_engine* e) {
   for (auto* b : bufs) b->release();
   for (auto& b : e->stage) b.release();
   if (e->arena) cudaFree(e->arena);
+  if (e->img_arena) cudaFree(e->img_arena);
   delete e;
 }
 
@@ -449,6 +497,15 @@ struct Prof {
   ~Prof() { if (on) { cudaEventRecord(ev.b, st); e->events.push_back(ev); } }
 };
 
+// per-edge MLP dispatch: tensor-core path for the 128-wide MLPs (hk, hv, xk), FFMA path for xv (16 outputs) or when forced
+void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
+              long long n_rows, int K, const TdMlp& m, const float* offsets, float coeff, float* out, cudaStream_t st) {
+  if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
+    td_launch_edge_mlp_tc(P, xm, src, etype, row_nodes, n_rows, K, m, m.w2_img, e->mlp_mode, offsets, coeff, out, e->sm_count, st);
+  else
+    td_launch_edge_mlp(P, xm, src, etype, row_nodes, n_rows, K, m, offsets, coeff, out, e->sm_count, st);
+}
+
 // One evaluation of the network on the bound batch (reference ScorePosNet3D.forward -> UniTransformerO2TwoUpdateGeneral.forward)
 void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
   const int N = e->N, Nl = e->Nl, K = e->K;
@@ -472,8 +529,8 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     td_launch_node_q(P, N, ly.x2h.q, q, st);
     {
       Prof pr(e, st, EV_EDGE_MLP);
-      td_launch_edge_mlp(P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), e->sm_count, st);
-      td_launch_edge_mlp(P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), e->sm_count, st);
+      edge_mlp(e, P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st);
+      edge_mlp(e, P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), st);
     }
     {
       Prof pr(e, st, EV_AGG_H);
@@ -486,10 +543,8 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     td_launch_node_q(P, N, ly.h2x.q, q, st);
     {
       Prof pr(e, st, EV_EDGE_MLP);
-      td_launch_edge_mlp(P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.k, ly.offsets, ly.coeff, e->kbuf.as<float>(),
-                         e->sm_count, st);
-      td_launch_edge_mlp(P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.v, ly.offsets, ly.coeff, e->v16.as<float>(),
-                         e->sm_count, st);
+      edge_mlp(e, P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st);
+      edge_mlp(e, P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.v, ly.offsets, ly.coeff, e->v16.as<float>(), st);
     }
     {
       Prof pr(e, st, EV_AGG_X);

@@ -66,3 +66,23 @@ void td_launch_edge_const(const float4* xm, const int* src, int n_nodes, int k, 
   edge_const_kernel<<<(int)blocks, EC_WARPS * 32, 0, st>>>(xm, src, n_slots, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2,
                                                             etype, e_w);
 }
+
+// Per-layer edge length |x_dst - x_src| (reference models/uni_transformer.py:188-189) for every slot, from the layer's input
+// coordinates; consumed by the tensor-core edge-MLP producers so that their metadata loads are plain coalesced streams.
+__global__ void edge_geom_kernel(const float4* __restrict__ xm, const int* __restrict__ src, long long n_slots, int k, float* __restrict__ dist) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_slots) return;
+  const int s = src[e];
+  float d = 0.0f;
+  if (s >= 0) {
+    const float4 xd = xm[e / k], xs = xm[s];
+    const float dx = xd.x - xs.x, dy = xd.y - xs.y, dz = xd.z - xs.z;
+    d = sqrtf(dx * dx + dy * dy + dz * dz);
+  }
+  dist[e] = d;
+}
+
+void td_launch_edge_geom(const float4* xm, const int* src, int n_nodes, int k, float* dist, cudaStream_t st) {
+  const long long n = (long long)n_nodes * k;
+  if (n > 0) edge_geom_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(xm, src, n, k, dist);
+}

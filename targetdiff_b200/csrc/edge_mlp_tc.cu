@@ -8,10 +8,11 @@
 //     kind::f16 passes accumulating in fp32 in TMEM:  a1b1 + a1b2 + a2b1 (+ a1b3 + a2b2 + a3b1).
 //     NP=3 keeps 24 mantissa bits of both operands (error ~2^-22, i.e. fp32 GEMM class); NP=2 keeps 16.
 //     Plain TF32 / BF16 single-pass MMA would break the 1e-4 position tolerance.
-//   * warp-specialised persistent CTA (one per SM), 13 warps:
+//   * warp-specialised persistent CTA (one per SM), roles aligned to warpgroups so setmaxnreg can hand registers to producers:
 //       warps 0-3   epilogue: tcgen05.ld accumulator rows (warp q owns TMEM lanes 32q..32q+31) -> +bias -> global
-//       warp  4     TMEM allocator + single-thread MMA issuer (tcgen05.mma / tcgen05.commit)
-//       warps 5-12  producers: 8 edge rows per warp in registers -- coalesced 512 B gathers of the projected node
+//       warp  4     TMEM allocator + single-thread MMA issuer (tcgen05.mma / tcgen05.commit); warps 5-7 idle
+//       warps 8..   producers, 8 warps per set (NSETS sets work on different tiles concurrently):
+//                   8 edge rows per warp in registers -- coalesced 512 B gathers of the projected node
 //                   rows, gaussians by 4 lanes per row, type/gaussian table through L1 (one table row feeds 8 edge rows),
 //                   LayerNorm by shuffles, ReLU, bf16 split, 8-byte stores into the UMMA K-major SWIZZLE_128B layout
 //     mbarriers: a_full/a_empty (producers <-> MMA), d_full/d_empty (MMA <-> epilogue, accumulator double-buffered in TMEM).
@@ -22,11 +23,11 @@
 
 namespace {
 
-constexpr int kEpiWarps = 4;
-constexpr int kMmaWarp = 4;
-constexpr int kProdWarp0 = 5;
-constexpr int kProdWarps = 8;
-constexpr int kThreads = (kProdWarp0 + kProdWarps) * 32;   // 416
+// warp roles (warpgroup-aligned so that setmaxnreg can move registers from the light roles to the producers)
+constexpr int kEpiWarps = 4;       // warps 0-3
+constexpr int kMmaWarp = 4;        // warp 4 (warps 5-7 idle: they only keep the warpgroup aligned)
+constexpr int kProdWarp0 = 8;      // warps 8.. : producers, 8 warps per producer set
+constexpr int kProdWarps = 8;      // warps per producer set == arrivals per activation tile
 constexpr int kPieceBytes = 128 * 128 * 2;                 // one bf16 piece of a 128x128 tile
 constexpr int kAtomBytes = 128 * 128;                      // 128 rows x 64 bf16 (128 B) : one K-half
 
@@ -104,6 +105,14 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
   return d;
 }
 
+// packed fp32 FMA (Blackwell FFMA2): (d0, d1) += w * (a0, a1)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float w, float a0, float a1) {
+  asm("{\n\t.reg .b64 ww, aa, dd;\n\tmov.b64 ww, {%2, %2};\n\tmov.b64 aa, {%3, %4};\n\tmov.b64 dd, {%0, %1};\n\t"
+      "fma.rn.f32x2 dd, ww, aa, dd;\n\tmov.b64 {%0, %1}, dd;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(w), "f"(a0), "f"(a1));
+}
+
 template <int NP>
 __device__ __forceinline__ void split_store_row(unsigned char* a_tile, int row, int lane, const float (&y)[4]) {
   // features 4*lane .. 4*lane+3 of `row` -> NP pieces; byte offset inside a piece (K-major SWIZZLE_128B, two K-halves)
@@ -121,11 +130,26 @@ __device__ __forceinline__ void split_store_row(unsigned char* a_tile, int row, 
 
 }  // namespace
 
-template <int NP, int NBUF>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int REGS> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {   // for roles that are not on the critical path
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(200);
+  }
+}
+
+template <int NP, int NBUF, int NSETS>
+__global__ void __launch_bounds__((kProdWarp0 + kProdWarps * NSETS) * 32, 1)
 edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, const int* __restrict__ src,
-                   const unsigned char* __restrict__ etype, const int* __restrict__ row_nodes, long long n_rows, int k, TdMlp m,
-                   const unsigned char* __restrict__ w2_image, const float* __restrict__ offsets, float coeff, float* __restrict__ out) {
+                   const unsigned char* __restrict__ etype, const float* __restrict__ dist_arr, const int* __restrict__ row_nodes,
+                   long long n_rows, int k, TdMlp m, const unsigned char* __restrict__ w2_image, const float* __restrict__ offsets, float coeff,
+                   float* __restrict__ out) {
   extern __shared__ unsigned char smem_raw[];
   // carve (1024-byte aligned: SWIZZLE_128B atoms)
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -141,6 +165,8 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // ---- one-time setup: weights image -> smem, params, barriers, TMEM
+  constexpr int kThreads = (kProdWarp0 + kProdWarps * NSETS) * 32;
+  static_assert(NBUF >= NSETS, "every producer set needs its own activation buffer");
   for (int i = tid; i < NP * kPieceBytes / 16; i += kThreads)
     reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(w2_image)[i];
   for (int i = tid; i < TD_H; i += kThreads) { s_b2[i] = m.b2[i]; s_g[i] = m.ln_g[i]; s_b[i] = m.ln_b[i]; }
@@ -167,120 +193,144 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
 
   if (warp >= kProdWarp0) {
     // =============================================================== producers
-    const int pw = warp - kProdWarp0;            // 0..7, owns rows pw*16 .. pw*16+15 of the tile (two groups of 8)
-    const int rsub = lane >> 2, jq = lane & 3;   // metadata: lane handles row `rsub` of the group, gaussians 5*jq .. 5*jq+4
+    // Producer set `ps` (8 warps) builds the activation tiles of the CTA's local tiles it = ps, ps+NSETS, ...; inside a set,
+    // warp pw owns rows pw*16 .. pw*16+15 as two "groups" of 8 rows held in registers.
+    if (NSETS > 1) reg_inc<96>();
+    const int ps = (warp - kProdWarp0) / kProdWarps, pw = (warp - kProdWarp0) % kProdWarps;
+    const int rsub = lane >> 2, jq = lane & 3;   // metadata: 4 lanes per row; lane holds gaussians 5*jq .. 5*jq+4 of row rsub
     float mu[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) mu[i] = offsets[5 * jq + i];
-    for (long long it = 0; it < my_tiles; ++it) {
-      const long long tile = blockIdx.x + it * gridDim.x;
-      const int buf = (int)(it % NBUF);
-      const uint32_t ph = (uint32_t)((it / NBUF) & 1);
-      mbar_wait(bar_a_empty + 8 * buf, ph ^ 1);          // first use of a buffer passes immediately
-      unsigned char* a_tile = sA + buf * NP * kPieceBytes;
-#pragma unroll 1
-      for (int grp = 0; grp < 2; ++grp) {
-        const int r0 = pw * 16 + grp * 8;
-        // ---- per-row metadata, 4 lanes per row
-        const long long idx = tile * 128 + r0 + rsub;
-        int s = -1, dst = 0, ty = 0;
-        float g[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        if (idx < n_rows) {
-          const long long a = idx / k;
-          const int j = (int)(idx - a * k);
-          dst = row_nodes ? row_nodes[a] : (int)a;
-          const long long e = (long long)dst * k + j;
-          s = src[e];
-          if (s >= 0) {
-            ty = etype[e];
-            const float4 xd = xm[dst], xs = xm[s];
-            const float dx = xd.x - xs.x, dy = xd.y - xs.y, dz = xd.z - xs.z;
-            const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              const float t = dist - mu[i];
-              g[i] = expf(coeff * (t * t));
-            }
-          }
-        }
-        // ---- gathers: acc[r] = P[dst_r, offA + 4l..] + P[src_r, offB + 4l..]   (512 B coalesced per row)
-        float acc[8][4];
-        int s_r[8], t_r[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          s_r[r] = __shfl_sync(0xffffffffu, s, r * 4);
-          t_r[r] = __shfl_sync(0xffffffffu, ty, r * 4);
-          const int d_r = __shfl_sync(0xffffffffu, dst, r * 4);
-          if (s_r[r] >= 0) {
-            const float4 pa = *reinterpret_cast<const float4*>(P + (size_t)d_r * TD_NPROJ + m.offA + 4 * lane);
-            const float4 pb = *reinterpret_cast<const float4*>(P + (size_t)s_r[r] * TD_NPROJ + m.offB + 4 * lane);
-            acc[r][0] = pa.x + pb.x; acc[r][1] = pa.y + pb.y; acc[r][2] = pa.z + pb.z; acc[r][3] = pa.w + pb.w;
-          } else {
-            acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
-          }
-        }
-        // ---- type / gaussian block of the first Linear: one table row (L1) feeds the 8 edge rows of the group
-        unsigned present = 0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) present |= (s_r[r] >= 0) ? (1u << t_r[r]) : 0u;
-#pragma unroll 1
-        for (int t = 0; t < 4; ++t) {
-          if (!((present >> t) & 1u)) continue;
-          const float* tb = m.tab + (size_t)t * TD_TAB * TD_H + 4 * lane;
-          const bool mine = (s >= 0) && (ty == t);
-          {
-            const float4 c = __ldg(reinterpret_cast<const float4*>(tb + TD_NG * TD_H));     // type column + bias
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const float w = (s_r[r] >= 0 && t_r[r] == t) ? 1.0f : 0.0f;
-              acc[r][0] = fmaf(w, c.x, acc[r][0]); acc[r][1] = fmaf(w, c.y, acc[r][1]);
-              acc[r][2] = fmaf(w, c.z, acc[r][2]); acc[r][3] = fmaf(w, c.w, acc[r][3]);
-            }
-          }
-#pragma unroll
-          for (int jj = 0; jj < TD_NG; ++jj) {
-            const float4 c = __ldg(reinterpret_cast<const float4*>(tb + jj * TD_H));
-            const float gm = mine ? g[jj % 5] : 0.0f;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const float w = __shfl_sync(0xffffffffu, gm, r * 4 + jj / 5);
-              acc[r][0] = fmaf(w, c.x, acc[r][0]); acc[r][1] = fmaf(w, c.y, acc[r][1]);
-              acc[r][2] = fmaf(w, c.z, acc[r][2]); acc[r][3] = fmaf(w, c.w, acc[r][3]);
-            }
-          }
-        }
-        // ---- LayerNorm + ReLU + bf16 split + swizzled store
-        const float4 g4 = *reinterpret_cast<const float4*>(s_g + 4 * lane);
-        const float4 b4 = *reinterpret_cast<const float4*>(s_b + 4 * lane);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          float y[4] = {0.f, 0.f, 0.f, 0.f};
-          if (s_r[r] >= 0) {
-            const float mean = warp_sum((acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3])) * (1.0f / 128.0f);
-            const float d0 = acc[r][0] - mean, d1 = acc[r][1] - mean, d2 = acc[r][2] - mean, d3 = acc[r][3] - mean;
-            const float var = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) * (1.0f / 128.0f);
-            const float rstd = 1.0f / sqrtf(var + 1e-5f);
-            y[0] = fmaxf(d0 * rstd * g4.x + b4.x, 0.f);
-            y[1] = fmaxf(d1 * rstd * g4.y + b4.y, 0.f);
-            y[2] = fmaxf(d2 * rstd * g4.z + b4.z, 0.f);
-            y[3] = fmaxf(d3 * rstd * g4.w + b4.w, 0.f);
-          }
-          split_store_row<NP>(a_tile, r0 + r, lane, y);
+    const long long n_my = (my_tiles > ps) ? (my_tiles - ps + NSETS - 1) / NSETS : 0;   // tiles of this set
+    const long long n_groups = n_my * 2;
+
+    auto load_md = [&](long long q, int& s_, int& ty_, int& dst_, float& dist_) {
+      s_ = -1; ty_ = 0; dst_ = 0; dist_ = 0.f;
+      if (q < n_groups) {
+        const long long tile = blockIdx.x + (ps + (q >> 1) * NSETS) * (long long)gridDim.x;
+        const long long idx64 = tile * 128 + pw * 16 + (int)(q & 1) * 8 + rsub;
+        if (idx64 < n_rows) {
+          const unsigned idx = (unsigned)idx64;
+          const unsigned a = idx / (unsigned)k;
+          const int j = (int)(idx - a * (unsigned)k);
+          dst_ = row_nodes ? row_nodes[a] : (int)a;
+          const size_t e = (size_t)dst_ * k + j;
+          s_ = src[e];
+          ty_ = etype[e];
+          dist_ = dist_arr[e];
         }
       }
-      fence_proxy_async();          // activation tile -> visible to the tensor-core proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_a_full + 8 * buf);
+    };
+    int s0, t0, d0, s1, t1, d1;
+    float dist0, dist1;
+    load_md(0, s0, t0, d0, dist0);
+#pragma unroll 1
+    for (long long q = 0; q < n_groups; ++q) {
+      load_md(q + 1, s1, t1, d1, dist1);        // coalesced metadata of the next group, consumed one iteration later
+      const long long it = ps + (q >> 1) * NSETS;
+      const int buf = (int)(it % NBUF);
+      const int r0 = pw * 16 + (int)(q & 1) * 8;
+      const bool valid = s0 >= 0;
+      // ---- gathers: acc[r] = P[src_r, offB + 4l..] (8 x 512 B coalesced rows), + P[dst, offA + 4l..]
+      float acc[8][4];
+      unsigned vmask = 0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int sr = __shfl_sync(0xffffffffu, s0, r * 4);
+        float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sr >= 0) {
+          vmask |= 1u << r;
+          pb = *reinterpret_cast<const float4*>(P + (size_t)sr * TD_NPROJ + m.offB + 4 * lane);
+        }
+        acc[r][0] = pb.x; acc[r][1] = pb.y; acc[r][2] = pb.z; acc[r][3] = pb.w;
+      }
+      const int dfirst = __shfl_sync(0xffffffffu, d0, 0);
+      if (__all_sync(0xffffffffu, !valid || d0 == dfirst)) {          // usual case (k % 8 == 0): one destination per group
+        const float4 pa = __ldg(reinterpret_cast<const float4*>(P + (size_t)dfirst * TD_NPROJ + m.offA + 4 * lane));
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if ((vmask >> r) & 1u) { acc[r][0] += pa.x; acc[r][1] += pa.y; acc[r][2] += pa.z; acc[r][3] += pa.w; }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int dr = __shfl_sync(0xffffffffu, d0, r * 4);
+          if ((vmask >> r) & 1u) {
+            const float4 pa = __ldg(reinterpret_cast<const float4*>(P + (size_t)dr * TD_NPROJ + m.offA + 4 * lane));
+            acc[r][0] += pa.x; acc[r][1] += pa.y; acc[r][2] += pa.z; acc[r][3] += pa.w;
+          }
+        }
+      }
+      float g[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const float t = dist0 - mu[i];
+        g[i] = valid ? expf(coeff * (t * t)) : 0.0f;
+      }
+      // ---- type / gaussian block of the first Linear: one table row (through L1) feeds the 8 edge rows of the group
+#pragma unroll 1
+      for (int t = 0; t < 4; ++t) {
+        const bool mine = valid && (t0 == t);
+        if (!__any_sync(0xffffffffu, mine)) continue;
+        const float* tb = m.tab + (size_t)t * TD_TAB * TD_H + 4 * lane;
+        {
+          const float4 c = __ldg(reinterpret_cast<const float4*>(tb + TD_NG * TD_H));       // type column + bias
+          const float wm = mine ? 1.0f : 0.0f;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float w = __shfl_sync(0xffffffffu, wm, r * 4);
+            ffma2(acc[r][0], acc[r][1], w, c.x, c.y);
+            ffma2(acc[r][2], acc[r][3], w, c.z, c.w);
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < TD_NG; ++jj) {
+          const float4 c = __ldg(reinterpret_cast<const float4*>(tb + jj * TD_H));
+          const float gm = mine ? g[jj % 5] : 0.0f;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float w = __shfl_sync(0xffffffffu, gm, r * 4 + jj / 5);
+            ffma2(acc[r][0], acc[r][1], w, c.x, c.y);
+            ffma2(acc[r][2], acc[r][3], w, c.z, c.w);
+          }
+        }
+      }
+      // ---- LayerNorm + ReLU (rows are independent: 8 interleaved shuffle chains)
+      const float4 g4 = *reinterpret_cast<const float4*>(s_g + 4 * lane);
+      const float4 b4 = *reinterpret_cast<const float4*>(s_b + 4 * lane);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float mean = warp_sum((acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3])) * (1.0f / 128.0f);
+        const float e0 = acc[r][0] - mean, e1 = acc[r][1] - mean, e2 = acc[r][2] - mean, e3 = acc[r][3] - mean;
+        const float var = warp_sum((e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3)) * (1.0f / 128.0f);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        const bool ok = (vmask >> r) & 1u;
+        acc[r][0] = ok ? fmaxf(e0 * rstd * g4.x + b4.x, 0.f) : 0.f;
+        acc[r][1] = ok ? fmaxf(e1 * rstd * g4.y + b4.y, 0.f) : 0.f;
+        acc[r][2] = ok ? fmaxf(e2 * rstd * g4.z + b4.z, 0.f) : 0.f;
+        acc[r][3] = ok ? fmaxf(e3 * rstd * g4.w + b4.w, 0.f) : 0.f;
+      }
+      // ---- bf16 split + swizzled store into the activation tile (wait for the tensor core to be done with the buffer)
+      if ((q & 1) == 0) mbar_wait(bar_a_empty + 8 * buf, (uint32_t)(((it / NBUF) & 1) ^ 1));
+      unsigned char* a_tile = sA + buf * NP * kPieceBytes;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) split_store_row<NP>(a_tile, r0 + r, lane, acc[r]);
+      if (q & 1) {
+        fence_proxy_async();          // activation tile -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_full + 8 * buf);
+      }
+      s0 = s1; t0 = t1; d0 = d1; dist0 = dist1;
     }
-  } else if (warp == kMmaWarp) {
-    // =============================================================== MMA issuer (one thread)
-    for (long long it = 0; it < my_tiles; ++it) {
+  } else if (warp >= kMmaWarp) {
+    // =============================================================== MMA issuer (one thread of warp 4; warps 5-7 idle)
+    if (NSETS > 1) reg_dec<32>();        // executed by the whole warpgroup (warps 4-7)
+    for (long long it = 0; warp == kMmaWarp && it < my_tiles; ++it) {
       const int buf = (int)(it % NBUF);
       const uint32_t pha = (uint32_t)((it / NBUF) & 1);
       const int db = (int)(it & 1);
       const uint32_t phd = (uint32_t)((it >> 1) & 1);
-      mbar_wait(bar_d_empty + 8 * db, phd ^ 1);          // accumulator buffer drained by the epilogue
-      mbar_wait(bar_a_full + 8 * buf, pha);              // activation tile written
+      mbar_wait_relaxed(bar_d_empty + 8 * db, phd ^ 1);  // accumulator buffer drained by the epilogue
+      mbar_wait_relaxed(bar_a_full + 8 * buf, pha);      // activation tile written
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(sA + buf * NP * kPieceBytes), b_addr = smem_u32(sB);
@@ -308,11 +358,12 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
     }
   } else {
     // =============================================================== epilogue (warps 0..3 <-> TMEM lanes 32w..32w+31)
+    if (NSETS > 1) reg_dec<64>();   // budget: 128*64 + 128*32 + 512*96 = 61440 = the 768 x 80 registers the CTA was launched with
     for (long long it = 0; it < my_tiles; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const int db = (int)(it & 1);
       const uint32_t phd = (uint32_t)((it >> 1) & 1);
-      mbar_wait(bar_d_full + 8 * db, phd);
+      mbar_wait_relaxed(bar_d_full + 8 * db, phd);
       tc_fence_after();
       const long long idx = tile * 128 + warp * 32 + lane;
       float* orow = out + (size_t)idx * 128;
@@ -345,26 +396,26 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
   }
 }
 
-template <int NP, int NBUF>
-static void launch_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes, long long n_rows,
-                      int k, TdMlp m, const unsigned char* w2_image, const float* offsets, float coeff, float* out, int sm_count,
+template <int NP, int NBUF, int NSETS>
+static void launch_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes,
+                      long long n_rows, int k, TdMlp m, const unsigned char* w2_image, const float* offsets, float coeff, float* out, int sm_count,
                       cudaStream_t st) {
   const size_t smem = 1024 + (size_t)NP * kPieceBytes + (size_t)NBUF * NP * kPieceBytes + 3 * TD_H * sizeof(float) + (2 * NBUF + 4) * 8 + 16;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(edge_mlp_tc_kernel<NP, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(edge_mlp_tc_kernel<NP, NBUF, NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
   const long long n_tiles = (n_rows + 127) / 128;
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
-  edge_mlp_tc_kernel<NP, NBUF><<<grid, kThreads, smem, st>>>(P, xm, src, etype, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out);
+  edge_mlp_tc_kernel<NP, NBUF, NSETS><<<grid, (kProdWarp0 + kProdWarps * NSETS) * 32, smem, st>>>(P, xm, src, etype, dist, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out);
 }
 
 // pieces = 3: 6-term product (fp32-class accuracy); pieces = 2: 3-term product (16 mantissa bits).  nout must be 128.
-void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
-                           long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
+void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const float* dist,
+                           const int* row_nodes, long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
                            float* out, int sm_count, cudaStream_t st) {
   if (n_rows == 0) return;
-  if (pieces == 2) launch_tc<2, 2>(P, xm, src, etype, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, sm_count, st);
-  else launch_tc<3, 1>(P, xm, src, etype, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, sm_count, st);
+  if (pieces == 2) launch_tc<2, 2, 2>(P, xm, src, etype, dist, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, sm_count, st);
+  else launch_tc<3, 1, 1>(P, xm, src, etype, dist, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, sm_count, st);
 }

@@ -73,7 +73,7 @@ struct tdiff_engine {
   bool bound = false, has_ligand = false, have_graph = false;
   int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
   DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
-  DevBuf xm0, xm1, offset, h0, h, P, q, src, etype, e_w, kbuf, vbuf, v16, lig_pos, lig_v, logits;
+  DevBuf xm0, xm1, offset, h0, h, P, q, src, etype, e_w, dist, kbuf, vbuf, v16, lig_pos, lig_v, logits;
   DevBuf step, err_flag, node_off, total_edges;
   DevBuf stage[8];   // staging for tdiff_sample_host
   // ---- instrumentation
@@ -369,7 +369,7 @@ extern "C" void tdiff_destroy(tdiff_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   DevBuf* bufs[] = {&e->node_ptr, &e->prot_ptr, &e->prot_node, &e->prot_graph, &e->lig_node, &e->lig_graph, &e->node_lig, &e->xm0, &e->xm1,
-                    &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->etype, &e->e_w, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
+                    &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->etype, &e->e_w, &e->dist, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
                     &e->lig_v, &e->logits, &e->step, &e->err_flag, &e->node_off, &e->total_edges};
   for (auto* b : bufs) b->release();
   for (auto& b : e->stage) b.release();
@@ -414,7 +414,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   bad |= e->lig_node.ensure(Nl * 4 + 4) | e->lig_graph.ensure(Nl * 4 + 4) | e->node_lig.ensure(N * 4);
   bad |= e->xm0.ensure(N * 16) | e->xm1.ensure(N * 16) | e->offset.ensure((size_t)B * 16);
   bad |= e->h0.ensure(N * TD_H * 4) | e->h.ensure(N * TD_H * 4) | e->P.ensure((size_t)N * TD_NPROJ * 4) | e->q.ensure(N * TD_H * 4);
-  bad |= e->src.ensure(slots * 4) | e->etype.ensure(slots) | e->e_w.ensure(slots * 4);
+  bad |= e->src.ensure(slots * 4) | e->etype.ensure(slots) | e->e_w.ensure(slots * 4) | e->dist.ensure(slots * 4);
   bad |= e->kbuf.ensure(slots * TD_H * 4) | e->vbuf.ensure(slots * TD_H * 4) | e->v16.ensure((size_t)Nl * K * TD_HEADS * 4 + 16);
   bad |= e->lig_pos.ensure(Nl * 16 + 16) | e->lig_v.ensure(Nl * 4 + 4) | e->logits.ensure((size_t)Nl * e->cfg.num_classes * 4 + 4);
   bad |= e->node_off.ensure(N * 8);
@@ -501,7 +501,7 @@ struct Prof {
 void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
               long long n_rows, int K, const TdMlp& m, const float* offsets, float coeff, float* out, cudaStream_t st) {
   if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
-    td_launch_edge_mlp_tc(P, xm, src, etype, row_nodes, n_rows, K, m, m.w2_img, e->mlp_mode, offsets, coeff, out, e->sm_count, st);
+    td_launch_edge_mlp_tc(P, xm, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, e->mlp_mode, offsets, coeff, out, e->sm_count, st);
   else
     td_launch_edge_mlp(P, xm, src, etype, row_nodes, n_rows, K, m, offsets, coeff, out, e->sm_count, st);
 }
@@ -527,6 +527,7 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     // ---- x2h: h <- h + sum_e alpha * v * e_w
     td_launch_node_proj(h, N, ly.x2h.wn_t, ly.x2h.bn, P, st);
     td_launch_node_q(P, N, ly.x2h.q, q, st);
+    if (e->mlp_mode != 0) { td_launch_edge_geom(xm[cur], src, N, K, e->dist.as<float>(), st); e->launches += 1; }
     {
       Prof pr(e, st, EV_EDGE_MLP);
       edge_mlp(e, P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st);

@@ -120,8 +120,9 @@ void td_launch_node_proj(const float* h, int n_nodes, const float* wn_t, const f
 void td_launch_node_q(const float* P, int n_nodes, TdMlp q, float* qout, cudaStream_t st);
 void td_launch_edge_mlp(const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
                         long long n_rows, int k, TdMlp m, const float* offsets, float coeff, float* out, int sm_count, cudaStream_t st);
-void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
-                           long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
+void td_launch_edge_geom(const float4* xm, const int* src, int n_nodes, int k, float* dist, cudaStream_t st);
+void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const float* dist,
+                           const int* row_nodes, long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
                            float* out, int sm_count, cudaStream_t st);
 void td_launch_aggregate_h(const float* kbuf, const float* vbuf, const float* e_w, const int* src, const float* q, const float* h_in,
                            float* h_out, int n_nodes, int k, cudaStream_t st);

@@ -62,7 +62,7 @@ struct tdiff_engine {
   // ---- weights (one device arena)
   float* arena = nullptr;
   unsigned char* img_arena = nullptr;   // bf16-split second-layer weights in the tensor-core shared-memory image
-  int mlp_mode = 3;                     // 0: FP32 FFMA (edge_mlp.cu), 2: tcgen05 3-term bf16 split, 3: tcgen05 6-term (fp32-class)
+  int mlp_mode = 2;                     // 0: FP32 FFMA (edge_mlp.cu), 2: tcgen05 2-piece bf16 split / 3 products (default), 3: 3-piece / 6 products
   std::vector<TdLayer> layers;
   const float *w_prot = nullptr, *b_prot = nullptr, *wl_t = nullptr, *bl = nullptr;
   const float *ew_w1t = nullptr, *ew_b1 = nullptr, *ew_g = nullptr, *ew_b = nullptr, *ew_w2 = nullptr, *ew_off = nullptr;

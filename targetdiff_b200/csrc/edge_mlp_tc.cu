@@ -144,12 +144,20 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
   }
 }
 
-template <int NP, int NBUF, int NSETS>
+// MODE 0: edge MLP (gathers + gaussian block + LN + ReLU -> second Linear), out [n_rows,128]
+// MODE 1: dense rows: out[:, y*128:(y+1)*128] = in[:, :128] . W_y^T + b_y for column block y = blockIdx.y (node projection)
+// MODE 2: LN rows:    out = relu(LN(in[:, in_off:in_off+128])) . W^T + b                                   (query MLP tail)
+struct TcRows {
+  const float* in;   // [n_rows, ldi]
+  int ldi, in_off, ldo;
+};
+
+template <int NP, int NBUF, int NSETS, int MODE>
 __global__ void __launch_bounds__((kProdWarp0 + kProdWarps * NSETS) * 32, 1)
 edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, const int* __restrict__ src,
                    const unsigned char* __restrict__ etype, const float* __restrict__ dist_arr, const int* __restrict__ row_nodes,
                    long long n_rows, int k, TdMlp m, const unsigned char* __restrict__ w2_image, const float* __restrict__ offsets, float coeff,
-                   float* __restrict__ out) {
+                   float* __restrict__ out, TcRows rw) {
   extern __shared__ unsigned char smem_raw[];
   // carve (1024-byte aligned: SWIZZLE_128B atoms)
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -168,8 +176,11 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
   constexpr int kThreads = (kProdWarp0 + kProdWarps * NSETS) * 32;
   static_assert(NBUF >= NSETS, "every producer set needs its own activation buffer");
   for (int i = tid; i < NP * kPieceBytes / 16; i += kThreads)
-    reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(w2_image)[i];
-  for (int i = tid; i < TD_H; i += kThreads) { s_b2[i] = m.b2[i]; s_g[i] = m.ln_g[i]; s_b[i] = m.ln_b[i]; }
+    reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(w2_image + (MODE == 1 ? (size_t)blockIdx.y * 3 * kPieceBytes : 0))[i];
+  for (int i = tid; i < TD_H; i += kThreads) {
+    s_b2[i] = m.b2[(MODE == 1 ? blockIdx.y * TD_H : 0) + i];
+    if (MODE != 1) { s_g[i] = m.ln_g[i]; s_b[i] = m.ln_b[i]; }
+  }
   if (tid == 0) {
     for (int i = 0; i < NBUF; ++i) {
       mbar_init(bar_a_full + 8 * i, kProdWarps);
@@ -197,6 +208,49 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
     // warp pw owns rows pw*16 .. pw*16+15 as two "groups" of 8 rows held in registers.
     if (NSETS > 1) reg_inc<96>();
     const int ps = (warp - kProdWarp0) / kProdWarps, pw = (warp - kProdWarp0) % kProdWarps;
+    if constexpr (MODE != 0) {
+      // ---- dense / LN row producers: 8 rows per warp-iteration straight from `in` (coalesced 512 B rows)
+      const long long n_my = (my_tiles > ps) ? (my_tiles - ps + NSETS - 1) / NSETS : 0;
+      const float4 g4 = MODE == 2 ? *reinterpret_cast<const float4*>(s_g + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b4 = MODE == 2 ? *reinterpret_cast<const float4*>(s_b + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (long long q = 0; q < n_my * 2; ++q) {
+        const long long it = ps + (q >> 1) * NSETS;
+        const int buf = (int)(it % NBUF);
+        const int r0 = pw * 16 + (int)(q & 1) * 8;
+        const long long row0 = (blockIdx.x + it * (long long)gridDim.x) * 128 + r0;
+        float acc[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row0 + r < n_rows) v = *reinterpret_cast<const float4*>(rw.in + (size_t)(row0 + r) * rw.ldi + rw.in_off + 4 * lane);
+          acc[r][0] = v.x; acc[r][1] = v.y; acc[r][2] = v.z; acc[r][3] = v.w;
+        }
+        if (MODE == 2) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float mean = warp_sum((acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3])) * (1.0f / 128.0f);
+            const float e0 = acc[r][0] - mean, e1 = acc[r][1] - mean, e2 = acc[r][2] - mean, e3 = acc[r][3] - mean;
+            const float var = warp_sum((e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3)) * (1.0f / 128.0f);
+            const float rstd = 1.0f / sqrtf(var + 1e-5f);
+            const bool ok = row0 + r < n_rows;
+            acc[r][0] = ok ? fmaxf(e0 * rstd * g4.x + b4.x, 0.f) : 0.f;
+            acc[r][1] = ok ? fmaxf(e1 * rstd * g4.y + b4.y, 0.f) : 0.f;
+            acc[r][2] = ok ? fmaxf(e2 * rstd * g4.z + b4.z, 0.f) : 0.f;
+            acc[r][3] = ok ? fmaxf(e3 * rstd * g4.w + b4.w, 0.f) : 0.f;
+          }
+        }
+        if ((q & 1) == 0) mbar_wait(bar_a_empty + 8 * buf, (uint32_t)(((it / NBUF) & 1) ^ 1));
+        unsigned char* a_tile = sA + buf * NP * kPieceBytes;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) split_store_row<NP>(a_tile, r0 + r, lane, acc[r]);
+        if (q & 1) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_a_full + 8 * buf);
+        }
+      }
+    } else {
     const int rsub = lane >> 2, jq = lane & 3;   // metadata: 4 lanes per row; lane holds gaussians 5*jq .. 5*jq+4 of row rsub
     float mu[5];
 #pragma unroll
@@ -321,6 +375,7 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
       }
       s0 = s1; t0 = t1; d0 = d1; dist0 = dist1;
     }
+    }
   } else if (warp >= kMmaWarp) {
     // =============================================================== MMA issuer (one thread of warp 4; warps 5-7 idle)
     if (NSETS > 1) reg_dec<32>();        // executed by the whole warpgroup (warps 4-7)
@@ -366,7 +421,7 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
       mbar_wait_relaxed(bar_d_full + 8 * db, phd);
       tc_fence_after();
       const long long idx = tile * 128 + warp * 32 + lane;
-      float* orow = out + (size_t)idx * 128;
+      float* orow = out + (size_t)idx * (MODE == 0 ? 128 : rw.ldo) + (MODE == 1 ? blockIdx.y * 128 : 0);
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t v[32];
@@ -396,19 +451,22 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
   }
 }
 
-template <int NP, int NBUF, int NSETS>
+template <int NP, int NBUF, int NSETS, int MODE>
 static void launch_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes,
-                      long long n_rows, int k, TdMlp m, const unsigned char* w2_image, const float* offsets, float coeff, float* out, int sm_count,
-                      cudaStream_t st) {
+                      long long n_rows, int k, TdMlp m, const unsigned char* w2_image, const float* offsets, float coeff, float* out, TcRows rw,
+                      int nblocks, int sm_count, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)NP * kPieceBytes + (size_t)NBUF * NP * kPieceBytes + 3 * TD_H * sizeof(float) + (2 * NBUF + 4) * 8 + 16;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(edge_mlp_tc_kernel<NP, NBUF, NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(edge_mlp_tc_kernel<NP, NBUF, NSETS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
   const long long n_tiles = (n_rows + 127) / 128;
-  const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
-  edge_mlp_tc_kernel<NP, NBUF, NSETS><<<grid, (kProdWarp0 + kProdWarps * NSETS) * 32, smem, st>>>(P, xm, src, etype, dist, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out);
+  int per = sm_count / nblocks;
+  if (per < 1) per = 1;
+  dim3 grid((unsigned)(n_tiles < per ? n_tiles : per), (unsigned)nblocks);
+  edge_mlp_tc_kernel<NP, NBUF, NSETS, MODE><<<grid, (kProdWarp0 + kProdWarps * NSETS) * 32, smem, st>>>(P, xm, src, etype, dist, row_nodes, n_rows, k,
+                                                                                                     m, w2_image, offsets, coeff, out, rw);
 }
 
 // pieces = 3: 6-term product (fp32-class accuracy); pieces = 2: 3-term product (16 mantissa bits).  nout must be 128.
@@ -416,6 +474,23 @@ void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, con
                            const int* row_nodes, long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
                            float* out, int sm_count, cudaStream_t st) {
   if (n_rows == 0) return;
-  if (pieces == 2) launch_tc<2, 2, 2>(P, xm, src, etype, dist, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, sm_count, st);
-  else launch_tc<3, 1, 1>(P, xm, src, etype, dist, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, sm_count, st);
+  TcRows rw = {nullptr, 0, 0, 128};
+  if (pieces == 2) launch_tc<2, 2, 2, 0>(P, xm, src, etype, dist, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, rw, 1, sm_count, st);
+  else launch_tc<3, 1, 1, 0>(P, xm, src, etype, dist, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, rw, 1, sm_count, st);
+}
+
+// Node-side GEMMs on the same tensor-core pipeline.
+//   mode 1: out[n_rows, nblocks*128] = in[n_rows,128] . W^T + bias, W given as `nblocks` images of [128 x 128] (node projection, nblocks = 5)
+//   mode 2: out[n_rows,128] = relu(LN(in[:, in_off:in_off+128]; m.ln_g, m.ln_b)) . W^T + m.b2                         (query MLP tail)
+void td_launch_rows_tc(int mode, const float* in, int ldi, int in_off, long long n_rows, TdMlp m, const unsigned char* w_image, int pieces, float* out,
+                       int ldo, int nblocks, int sm_count, cudaStream_t st) {
+  if (n_rows == 0) return;
+  TcRows rw = {in, ldi, in_off, ldo};
+  if (mode == 1) {
+    if (pieces == 2) launch_tc<2, 2, 2, 1>(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_rows, 1, m, w_image, nullptr, 0.f, out, rw, nblocks, sm_count, st);
+    else launch_tc<3, 1, 1, 1>(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_rows, 1, m, w_image, nullptr, 0.f, out, rw, nblocks, sm_count, st);
+  } else {
+    if (pieces == 2) launch_tc<2, 2, 2, 2>(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_rows, 1, m, w_image, nullptr, 0.f, out, rw, 1, sm_count, st);
+    else launch_tc<3, 1, 1, 2>(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_rows, 1, m, w_image, nullptr, 0.f, out, rw, 1, sm_count, st);
+  }
 }

@@ -167,7 +167,7 @@ bool pack_edge_mlp(Packer& pk, const std::string& p, int nout, MlpOff& o, const 
   return true;
 }
 
-struct SubOff { size_t wn_t, bn; MlpOff k, v, q; };
+struct SubOff { size_t wn_t, bn; long long wn_img; MlpOff k, v, q; };
 
 bool pack_sublayer(Packer& pk, const std::string& p, const char* kn, const char* vn, const char* qn, int nout_v, SubOff& so) {
   const int KV = 4 + 4 * TD_NG + 2 * TD_H;
@@ -182,7 +182,10 @@ bool pack_sublayer(Packer& pk, const std::string& p, const char* kn, const char*
   const float* w2q = pk.get(qp + ".net.3.weight", (int64_t)TD_H * TD_H);
   const float* b2q = pk.get(qp + ".net.3.bias", TD_H);
   if (!w1q || !b1q || !gq || !bq || !w2q || !b2q) return false;
-  so.q.nout = TD_H; so.q.tab = 0; so.q.img = -1;
+  so.q.nout = TD_H; so.q.tab = 0;
+  so.q.img = (long long)pk.img.size();
+  pk.img.resize(pk.img.size() + 3 * 32768, 0);
+  pack_umma_image(w2q, pk.img, (size_t)so.q.img);
   so.q.ln_g = pk.alloc(TD_H); memcpy(&pk.host[so.q.ln_g], gq, TD_H * sizeof(float));
   so.q.ln_b = pk.alloc(TD_H); memcpy(&pk.host[so.q.ln_b], bq, TD_H * sizeof(float));
   so.q.w2t = pk.alloc((size_t)TD_H * TD_H);
@@ -202,6 +205,15 @@ bool pack_sublayer(Packer& pk, const std::string& p, const char* kn, const char*
     }
   }
   for (int c = 0; c < TD_H; ++c) pk.host[so.bn + 512 + c] = b1q[c];
+  // tensor-core images of the five 128-column blocks of the node projection
+  so.wn_img = (long long)pk.img.size();
+  pk.img.resize(pk.img.size() + 5 * 3 * 32768, 0);
+  std::vector<float> blk((size_t)TD_H * TD_H);
+  for (int y = 0; y < 5; ++y) {
+    for (int n = 0; n < TD_H; ++n)
+      for (int kk = 0; kk < TD_H; ++kk) blk[(size_t)n * TD_H + kk] = pk.host[so.wn_t + (size_t)kk * TD_NPROJ + y * TD_H + n];
+    pack_umma_image(blk.data(), pk.img, (size_t)so.wn_img + (size_t)y * 3 * 32768);
+  }
   return true;
 }
 
@@ -343,9 +355,9 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
   for (int l = 0; l < L; ++l) {
     TdLayer& ly = e->layers[l];
     ly.offsets = A + o_off[l]; ly.coeff = coeffs[l];
-    ly.x2h.wn_t = A + sx[l].wn_t; ly.x2h.bn = A + sx[l].bn;
+    ly.x2h.wn_t = A + sx[l].wn_t; ly.x2h.bn = A + sx[l].bn; ly.x2h.wn_img = IM ? IM + sx[l].wn_img : nullptr;
     ly.x2h.k = mk_mlp(A, IM, sx[l].k, 0, 256); ly.x2h.v = mk_mlp(A, IM, sx[l].v, 128, 384); ly.x2h.q = mk_mlp(A, IM, sx[l].q, 512, 512);
-    ly.h2x.wn_t = A + sh[l].wn_t; ly.h2x.bn = A + sh[l].bn;
+    ly.h2x.wn_t = A + sh[l].wn_t; ly.h2x.bn = A + sh[l].bn; ly.h2x.wn_img = IM ? IM + sh[l].wn_img : nullptr;
     ly.h2x.k = mk_mlp(A, IM, sh[l].k, 0, 256); ly.h2x.v = mk_mlp(A, IM, sh[l].v, 128, 384); ly.h2x.q = mk_mlp(A, IM, sh[l].q, 512, 512);
   }
   if (e->step.ensure(sizeof(int)) || e->err_flag.ensure(sizeof(int)) || e->total_edges.ensure(sizeof(long long))) {
@@ -506,6 +518,19 @@ void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src,
     td_launch_edge_mlp(P, xm, src, etype, row_nodes, n_rows, K, m, offsets, coeff, out, e->sm_count, st);
 }
 
+// node-side GEMMs: P = h . Wn^T + bn ; q = relu(LN(P[:,512:640])) . W2q^T + b2q   (tensor cores unless TDIFF_EDGE_MLP=simt)
+void node_side(tdiff_engine* e, const float* h, int N, const TdSubLayer& sl, float* P, float* q, cudaStream_t st) {
+  if (e->mlp_mode != 0 && sl.wn_img && sl.q.w2_img) {
+    TdMlp pm = sl.q;
+    pm.b2 = sl.bn;                 // mode 1 reads the per-column-block bias through m.b2
+    td_launch_rows_tc(1, h, TD_H, 0, N, pm, sl.wn_img, e->mlp_mode, P, TD_NPROJ, TD_NPROJ / TD_H, e->sm_count, st);
+    td_launch_rows_tc(2, P, TD_NPROJ, 512, N, sl.q, sl.q.w2_img, e->mlp_mode, q, TD_H, 1, e->sm_count, st);
+  } else {
+    td_launch_node_proj(h, N, sl.wn_t, sl.bn, P, st);
+    td_launch_node_q(P, N, sl.q, q, st);
+  }
+}
+
 // One evaluation of the network on the bound batch (reference ScorePosNet3D.forward -> UniTransformerO2TwoUpdateGeneral.forward)
 void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
   const int N = e->N, Nl = e->Nl, K = e->K;
@@ -525,8 +550,7 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
   for (size_t l = 0; l < e->layers.size(); ++l) {
     const TdLayer& ly = e->layers[l];
     // ---- x2h: h <- h + sum_e alpha * v * e_w
-    td_launch_node_proj(h, N, ly.x2h.wn_t, ly.x2h.bn, P, st);
-    td_launch_node_q(P, N, ly.x2h.q, q, st);
+    node_side(e, h, N, ly.x2h, P, q, st);
     if (e->mlp_mode != 0) { td_launch_edge_geom(xm[cur], src, N, K, e->dist.as<float>(), st); e->launches += 1; }
     {
       Prof pr(e, st, EV_EDGE_MLP);
@@ -540,8 +564,7 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     e->launches += 5;
     if (fix_x || Nl == 0) continue;     // h2x only moves ligand atoms; with fix_x its result is discarded (:204-206)
     // ---- h2x: x_lig <- x_lig + mean_heads sum_e alpha * v * e_w * (x_dst - x_src), destinations = ligand atoms only
-    td_launch_node_proj(h, N, ly.h2x.wn_t, ly.h2x.bn, P, st);
-    td_launch_node_q(P, N, ly.h2x.q, q, st);
+    node_side(e, h, N, ly.h2x, P, q, st);
     {
       Prof pr(e, st, EV_EDGE_MLP);
       edge_mlp(e, P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st);

@@ -34,6 +34,7 @@ struct TdMlp {
 struct TdSubLayer {       // x2h or h2x
   const float* wn_t;      // [128][TD_NPROJ] node projection weights (transposed)
   const float* bn;        // [TD_NPROJ] bias (non-zero only in the q_pre block)
+  const unsigned char* wn_img;   // the same weights as 5 UMMA images of [128 x 128] (3 bf16 pieces each) for the tensor-core path
   TdMlp k, v, q;          // q.tab unused
 };
 
@@ -124,6 +125,8 @@ void td_launch_edge_geom(const float4* xm, const int* src, int n_nodes, int k, f
 void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const float* dist,
                            const int* row_nodes, long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
                            float* out, int sm_count, cudaStream_t st);
+void td_launch_rows_tc(int mode, const float* in, int ldi, int in_off, long long n_rows, TdMlp m, const unsigned char* w_image, int pieces, float* out,
+                       int ldo, int nblocks, int sm_count, cudaStream_t st);
 void td_launch_aggregate_h(const float* kbuf, const float* vbuf, const float* e_w, const int* src, const float* q, const float* h_in,
                            float* h_out, int n_nodes, int k, cudaStream_t st);
 void td_launch_aggregate_x(const float* kbuf, const float* v16, const float* e_w, const int* src, const float* q, const float4* xm_in,

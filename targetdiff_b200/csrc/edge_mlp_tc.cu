@@ -105,6 +105,22 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float hi, float lo) {
   return d;
 }
 
+// explicit shared-space accesses (the carve-up goes through uintptr_t, so plain dereferences would compile to generic LD/ST)
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// streaming 16-byte gather that does not allocate in L1 (keeps the L1-resident table / destination rows from being evicted)
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // packed fp32 FMA (Blackwell FFMA2): (d0, d1) += w * (a0, a1)
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float w, float a0, float a1) {
   asm("{\n\t.reg .b64 ww, aa, dd;\n\tmov.b64 ww, {%2, %2};\n\tmov.b64 aa, {%3, %4};\n\tmov.b64 dd, {%0, %1};\n\t"
@@ -114,7 +130,7 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float w, float a0, f
 }
 
 template <int NP>
-__device__ __forceinline__ void split_store_row(unsigned char* a_tile, int row, int lane, const float (&y)[4]) {
+__device__ __forceinline__ void split_store_row(uint32_t a_tile, int row, int lane, const float (&y)[4]) {
   // features 4*lane .. 4*lane+3 of `row` -> NP pieces; byte offset inside a piece (K-major SWIZZLE_128B, two K-halves)
   const int khalf = lane >> 4, chunk = (lane & 15) >> 1;
   const uint32_t off = khalf * kAtomBytes + row * 128 + ((chunk ^ (row & 7)) << 4) + ((lane & 1) << 3);
@@ -124,7 +140,7 @@ __device__ __forceinline__ void split_store_row(unsigned char* a_tile, int row, 
     const uint2 v = make_uint2(cvt_bf16x2(r[1], r[0]), cvt_bf16x2(r[3], r[2]));
     r[0] -= __uint_as_float(v.x << 16); r[1] -= __uint_as_float(v.x & 0xffff0000u);       // residuals are exact in fp32
     r[2] -= __uint_as_float(v.y << 16); r[3] -= __uint_as_float(v.y & 0xffff0000u);
-    *reinterpret_cast<uint2*>(a_tile + p * kPieceBytes + off) = v;
+    sts64(a_tile + p * kPieceBytes + off, v);
   }
 }
 
@@ -211,8 +227,8 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
     if constexpr (MODE != 0) {
       // ---- dense / LN row producers: 8 rows per warp-iteration straight from `in` (coalesced 512 B rows)
       const long long n_my = (my_tiles > ps) ? (my_tiles - ps + NSETS - 1) / NSETS : 0;
-      const float4 g4 = MODE == 2 ? *reinterpret_cast<const float4*>(s_g + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 b4 = MODE == 2 ? *reinterpret_cast<const float4*>(s_b + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 g4 = MODE == 2 ? lds128(smem_u32(s_g + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b4 = MODE == 2 ? lds128(smem_u32(s_b + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
       for (long long q = 0; q < n_my * 2; ++q) {
         const long long it = ps + (q >> 1) * NSETS;
@@ -223,7 +239,7 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row0 + r < n_rows) v = *reinterpret_cast<const float4*>(rw.in + (size_t)(row0 + r) * rw.ldi + rw.in_off + 4 * lane);
+          if (row0 + r < n_rows) v = ldg_stream(rw.in + (size_t)(row0 + r) * rw.ldi + rw.in_off + 4 * lane);
           acc[r][0] = v.x; acc[r][1] = v.y; acc[r][2] = v.z; acc[r][3] = v.w;
         }
         if (MODE == 2) {
@@ -241,7 +257,7 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
           }
         }
         if ((q & 1) == 0) mbar_wait(bar_a_empty + 8 * buf, (uint32_t)(((it / NBUF) & 1) ^ 1));
-        unsigned char* a_tile = sA + buf * NP * kPieceBytes;
+        const uint32_t a_tile = smem_u32(sA) + buf * NP * kPieceBytes;
 #pragma unroll
         for (int r = 0; r < 8; ++r) split_store_row<NP>(a_tile, r0 + r, lane, acc[r]);
         if (q & 1) {
@@ -294,7 +310,7 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
         float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (sr >= 0) {
           vmask |= 1u << r;
-          pb = *reinterpret_cast<const float4*>(P + (size_t)sr * TD_NPROJ + m.offB + 4 * lane);
+          pb = __ldg(reinterpret_cast<const float4*>(P + (size_t)sr * TD_NPROJ + m.offB + 4 * lane));   // neighbour lists overlap: L1 reuse
         }
         acc[r][0] = pb.x; acc[r][1] = pb.y; acc[r][2] = pb.z; acc[r][3] = pb.w;
       }
@@ -349,8 +365,8 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
         }
       }
       // ---- LayerNorm + ReLU (rows are independent: 8 interleaved shuffle chains)
-      const float4 g4 = *reinterpret_cast<const float4*>(s_g + 4 * lane);
-      const float4 b4 = *reinterpret_cast<const float4*>(s_b + 4 * lane);
+      const float4 g4 = lds128(smem_u32(s_g + 4 * lane));
+      const float4 b4 = lds128(smem_u32(s_b + 4 * lane));
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         const float mean = warp_sum((acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3])) * (1.0f / 128.0f);
@@ -365,7 +381,7 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
       }
       // ---- bf16 split + swizzled store into the activation tile (wait for the tensor core to be done with the buffer)
       if ((q & 1) == 0) mbar_wait(bar_a_empty + 8 * buf, (uint32_t)(((it / NBUF) & 1) ^ 1));
-      unsigned char* a_tile = sA + buf * NP * kPieceBytes;
+      const uint32_t a_tile = smem_u32(sA) + buf * NP * kPieceBytes;
 #pragma unroll
       for (int r = 0; r < 8; ++r) split_store_row<NP>(a_tile, r0 + r, lane, acc[r]);
       if (q & 1) {
@@ -429,7 +445,7 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
         if (idx < n_rows) {
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
-            const float4 bia = *reinterpret_cast<const float4*>(s_b2 + c0 + c);
+            const float4 bia = lds128(smem_u32(s_b2 + c0 + c));
             float4 o;
             o.x = __uint_as_float(v[c]) + bia.x; o.y = __uint_as_float(v[c + 1]) + bia.y;
             o.z = __uint_as_float(v[c + 2]) + bia.z; o.w = __uint_as_float(v[c + 3]) + bia.w;

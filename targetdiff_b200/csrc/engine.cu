@@ -61,8 +61,10 @@ struct tdiff_engine {
   int device = 0, sm_count = 148;
   // ---- weights (one device arena)
   float* arena = nullptr;
+  std::vector<float> host_arena;        // host copy of the packed fp32 weights (kernel-argument constants are read from it)
   unsigned char* img_arena = nullptr;   // bf16-split second-layer weights in the tensor-core shared-memory image
   int mlp_mode = 2;                     // 0: FP32 FFMA (edge_mlp.cu), 2: tcgen05 2-piece bf16 split / 3 products (default), 3: 3-piece / 6 products
+  bool mlp_v3 = true;                   // mode 2 edge MLPs: edge_mlp_v3.cu (both Linear layers on tcgen05) instead of edge_mlp_tc.cu
   std::vector<TdLayer> layers;
   const float *w_prot = nullptr, *b_prot = nullptr, *wl_t = nullptr, *bl = nullptr;
   const float *ew_w1t = nullptr, *ew_b1 = nullptr, *ew_g = nullptr, *ew_b = nullptr, *ew_w2 = nullptr, *ew_off = nullptr;
@@ -73,7 +75,7 @@ struct tdiff_engine {
   bool bound = false, has_ligand = false, have_graph = false;
   int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
   DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
-  DevBuf xm0, xm1, offset, h0, h, P, q, src, etype, e_w, dist, kbuf, vbuf, v16, lig_pos, lig_v, logits;
+  DevBuf xm0, xm1, offset, h0, h, P, q, src, etype, e_w, dist, tslow, kbuf, vbuf, v16, lig_pos, lig_v, logits;
   DevBuf step, err_flag, node_off, total_edges;
   DevBuf stage[8];   // staging for tdiff_sample_host
   // ---- instrumentation
@@ -108,7 +110,7 @@ struct Packer {
   }
 };
 
-struct MlpOff { size_t tab, ln_g, ln_b, w2t, b2; int nout; long long img; };
+struct MlpOff { size_t tab, ln_g, ln_b, w2t, b2; int nout; long long img, tab3; };
 
 // round-to-nearest-even fp32 -> bf16 bit pattern
 inline uint16_t bf16_rn(float x) {
@@ -130,6 +132,25 @@ void pack_umma_image(const float* w2, std::vector<unsigned char>& img, size_t of
         const uint16_t b = bf16_rn(r);
         r = r - bf16_f(b);
         memcpy(&img[off + (size_t)p * 32768 + o], &b, 2);
+      }
+    }
+}
+
+// Type-3 gaussian/type block as the B operand of the small "pre" MMA of edge_mlp_v3.cu: [128 out (N) x 32 K-slots] bf16 pieces,
+// K-major SWIZZLE_64B (64-byte rows, 8-row groups of 512 B, 16-byte chunk index XOR (row/2)%4).
+// K slots: 8*c + i = gaussian 5*c + i (c < 4, i < 5), slot 29 = constant row (type column + bias), all other slots 0.
+void pack_tab3_image(const float* tab3 /*[21][128]*/, std::vector<unsigned char>& img, size_t off) {
+  for (int n = 0; n < 128; ++n)
+    for (int slot = 0; slot < 32; ++slot) {
+      int j = -1;
+      if ((slot & 7) < 5) j = 5 * (slot >> 3) + (slot & 7);
+      else if (slot == 29) j = 20;
+      float r = j >= 0 ? tab3[(size_t)j * 128 + n] : 0.0f;
+      const size_t o = (size_t)(n >> 3) * 512 + (size_t)(n & 7) * 64 + (size_t)((((slot >> 3)) ^ ((n >> 1) & 3)) * 16) + (size_t)(slot & 7) * 2;
+      for (int p = 0; p < 3; ++p) {
+        const uint16_t b = bf16_rn(r);
+        r = r - bf16_f(b);
+        memcpy(&img[off + (size_t)p * 8192 + o], &b, 2);
       }
     }
 }
@@ -157,11 +178,14 @@ bool pack_edge_mlp(Packer& pk, const std::string& p, int nout, MlpOff& o, const 
   for (int kk = 0; kk < TD_H; ++kk)
     for (int n = 0; n < nout; ++n) pk.host[o.w2t + (size_t)kk * nout + n] = w2[(size_t)n * TD_H + kk];
   o.b2 = pk.alloc(nout); memcpy(&pk.host[o.b2], b2, nout * sizeof(float));
-  o.img = -1;
+  o.img = -1; o.tab3 = -1;
   if (nout == TD_H) {
     o.img = (long long)pk.img.size();
     pk.img.resize(pk.img.size() + 3 * 32768, 0);
     pack_umma_image(w2, pk.img, (size_t)o.img);
+    o.tab3 = (long long)pk.img.size();
+    pk.img.resize(pk.img.size() + 3 * 8192, 0);
+    pack_tab3_image(&pk.host[o.tab + (size_t)3 * TD_TAB * TD_H], pk.img, (size_t)o.tab3);
   }
   *w1_out = w1;
   return true;
@@ -182,7 +206,7 @@ bool pack_sublayer(Packer& pk, const std::string& p, const char* kn, const char*
   const float* w2q = pk.get(qp + ".net.3.weight", (int64_t)TD_H * TD_H);
   const float* b2q = pk.get(qp + ".net.3.bias", TD_H);
   if (!w1q || !b1q || !gq || !bq || !w2q || !b2q) return false;
-  so.q.nout = TD_H; so.q.tab = 0;
+  so.q.nout = TD_H; so.q.tab = 0; so.q.tab3 = -1;
   so.q.img = (long long)pk.img.size();
   pk.img.resize(pk.img.size() + 3 * 32768, 0);
   pack_umma_image(w2q, pk.img, (size_t)so.q.img);
@@ -220,6 +244,7 @@ bool pack_sublayer(Packer& pk, const std::string& p, const char* kn, const char*
 TdMlp mk_mlp(const float* base, const unsigned char* img_base, const MlpOff& o, int offA, int offB) {
   TdMlp m;
   m.w2_img = (o.img >= 0 && img_base) ? img_base + o.img : nullptr;
+  m.tab3_img = (o.tab3 >= 0 && img_base) ? img_base + o.tab3 : nullptr;
   m.tab = base + o.tab; m.ln_g = base + o.ln_g; m.ln_b = base + o.ln_b; m.w2t = base + o.w2t; m.b2 = base + o.b2;
   m.nout = o.nout; m.offA = offA; m.offB = offB;
   return m;
@@ -341,9 +366,11 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
   if (const char* mode = getenv("TDIFF_EDGE_MLP")) {
     if (!strcmp(mode, "simt")) e->mlp_mode = 0;
     else if (!strcmp(mode, "tc3")) e->mlp_mode = 2;
+    else if (!strcmp(mode, "tc3v2")) { e->mlp_mode = 2; e->mlp_v3 = false; }
     else if (!strcmp(mode, "tc6")) e->mlp_mode = 3;
-    else { cudaFree(e->arena); cudaFree(e->img_arena); delete e; return set_err(TDIFF_EINVAL, "TDIFF_EDGE_MLP=%s (simt|tc3|tc6)", mode); }
+    else { cudaFree(e->arena); cudaFree(e->img_arena); delete e; return set_err(TDIFF_EINVAL, "TDIFF_EDGE_MLP=%s (simt|tc3|tc3v2|tc6)", mode); }
   }
+  e->host_arena = pk.host;
   const float* A = e->arena;
   const unsigned char* IM = e->img_arena;
   e->t_c0 = A + tabs[0].off; e->t_ct = A + tabs[1].off; e->t_logvar = A + tabs[2].off; e->t_la = A + tabs[3].off;
@@ -381,7 +408,7 @@ extern "C" void tdiff_destroy(tdiff_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   DevBuf* bufs[] = {&e->node_ptr, &e->prot_ptr, &e->prot_node, &e->prot_graph, &e->lig_node, &e->lig_graph, &e->node_lig, &e->xm0, &e->xm1,
-                    &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->etype, &e->e_w, &e->dist, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
+                    &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
                     &e->lig_v, &e->logits, &e->step, &e->err_flag, &e->node_off, &e->total_edges};
   for (auto* b : bufs) b->release();
   for (auto& b : e->stage) b.release();
@@ -427,6 +454,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   bad |= e->xm0.ensure(N * 16) | e->xm1.ensure(N * 16) | e->offset.ensure((size_t)B * 16);
   bad |= e->h0.ensure(N * TD_H * 4) | e->h.ensure(N * TD_H * 4) | e->P.ensure((size_t)N * TD_NPROJ * 4) | e->q.ensure(N * TD_H * 4);
   bad |= e->src.ensure(slots * 4) | e->etype.ensure(slots) | e->e_w.ensure(slots * 4) | e->dist.ensure(slots * 4);
+  if (e->mlp_mode == 2 && e->mlp_v3) bad |= e->tslow.ensure(slots * TD_H * 4);   // row-indexed, only ligand-touching rows are touched
   bad |= e->kbuf.ensure(slots * TD_H * 4) | e->vbuf.ensure(slots * TD_H * 4) | e->v16.ensure((size_t)Nl * K * TD_HEADS * 4 + 16);
   bad |= e->lig_pos.ensure(Nl * 16 + 16) | e->lig_v.ensure(Nl * 4 + 4) | e->logits.ensure((size_t)Nl * e->cfg.num_classes * 4 + 4);
   bad |= e->node_off.ensure(N * 8);
@@ -512,7 +540,10 @@ struct Prof {
 // per-edge MLP dispatch: tensor-core path for the 128-wide MLPs (hk, hv, xk), FFMA path for xv (16 outputs) or when forced
 void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
               long long n_rows, int K, const TdMlp& m, const float* offsets, float coeff, float* out, cudaStream_t st) {
-  if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
+  if (e->mlp_mode == 2 && e->mlp_v3 && m.nout == TD_H && m.w2_img && m.tab3_img)
+    td_launch_edge_mlp_v3(P, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, m.tab3_img, offsets, coeff,
+                          e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena), e->tslow.as<float>(), out, e->sm_count, st);
+  else if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
     td_launch_edge_mlp_tc(P, xm, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, e->mlp_mode, offsets, coeff, out, e->sm_count, st);
   else
     td_launch_edge_mlp(P, xm, src, etype, row_nodes, n_rows, K, m, offsets, coeff, out, e->sm_count, st);

@@ -29,6 +29,7 @@ struct TdMlp {
   int nout;            // 128 or 16
   int offA, offB;      // column offsets into the node projection P
   const unsigned char* w2_img;   // nout==128 edge MLPs: second Linear as 3 bf16 pieces in the UMMA K-major SWIZZLE_128B image
+  const unsigned char* tab3_img; // type-3 (protein-protein) gaussian/type block [128 x 32] as bf16 pieces, K-major SWIZZLE_64B image
 };
 
 struct TdSubLayer {       // x2h or h2x
@@ -125,6 +126,9 @@ void td_launch_edge_geom(const float4* xm, const int* src, int n_nodes, int k, f
 void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const float* dist,
                            const int* row_nodes, long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
                            float* out, int sm_count, cudaStream_t st);
+void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_rows,
+                           int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
+                           const float* h_ln_g, const float* h_ln_b, float* tslow, float* out, int sm_count, cudaStream_t st);
 void td_launch_rows_tc(int mode, const float* in, int ldi, int in_off, long long n_rows, TdMlp m, const unsigned char* w_image, int pieces, float* out,
                        int ldo, int nblocks, int sm_count, cudaStream_t st);
 void td_launch_aggregate_h(const float* kbuf, const float* vbuf, const float* e_w, const int* src, const float* q, const float* h_in,

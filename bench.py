@@ -268,17 +268,22 @@ def main():
         ms_x, n_x = vals[1].value, cnts[1].value
         ms_mlp, n_mlp = vals[2].value, cnts[2].value
         tot = vals[3].value
+        mode = lib.tdiff_edge_mlp_mode(eng)
+        fused = mode == 5
         if n_h:
             t_h = ms_h / n_h * 1e-3
-            bytes_h = E * 1028 + N * 1536                           # k 512 + v 512 + e_w 4 per edge; q, h, out per node
+            if fused:   # keys never reach HBM: per edge 16 logits (64 B) + v 512 + e_w 4; per node h in + out
+                bytes_h, kname = E * 580 + N * 1024, 'aggregate_h_logits_kernel (scatter_softmax->scatter_sum on fused logits, x2h)'
+            else:       # k 512 + v 512 + e_w 4 per edge; q, h, out per node
+                bytes_h, kname = E * 1028 + N * 1536, 'aggregate_h_kernel (fused scatter_softmax->scatter_sum, x2h)'
             ach = bytes_h / t_h / 1e9
-            roofline = {'kernel': 'aggregate_h_kernel (fused scatter_softmax->scatter_sum, x2h)', 'bound': 'hbm', 'achieved': ach,
+            roofline = {'kernel': kname, 'bound': 'hbm', 'achieved': ach,
                         'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
                         'algorithmic_bytes_per_launch': bytes_h, 'avg_launch_ms': t_h * 1e3, 'launches_timed': n_h,
                         'share_of_step': ms_h / tot if tot else None}
         if n_x:
             El = Nl * a.knn
-            bytes_x = El * 596 + Nl * 537
+            bytes_x = El * (148 if fused else 596) + Nl * (25 if fused else 537)
             t_x = ms_x / n_x * 1e-3
             extra['roofline_aggregate_x'] = {'kernel': 'aggregate_x_kernel (h2x, ligand destinations only)', 'bound': 'hbm',
                                              'achieved': bytes_x / t_x / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': bytes_x / t_x / 1e9 / peak,
@@ -288,7 +293,7 @@ def main():
             # (128*128 + 20*128) + (128*16 + 20*128) MAC
             flops = 2.0 * (E * 2 * (128 * 128 + 20 * 128) + Nl * a.knn * ((128 * 128 + 20 * 128) + (128 * 16 + 20 * 128)))
             t_m = ms_mlp / (n_mlp / 2) * 1e-3                       # per layer (x2h pair + h2x pair)
-            extra['edge_mlp'] = {'kernel': 'edge MLPs (tcgen05 bf16-split second Linear; mode %s)' % os.environ.get('TDIFF_EDGE_MLP', 'tc3'), 'executed_tflops': flops / t_m / 1e12,
+            extra['edge_mlp'] = {'kernel': 'edge MLPs (mode %d, see tdiff_edge_mlp_mode)' % mode, 'executed_tflops': flops / t_m / 1e12,
                                  'ms_per_layer': t_m * 1e3, 'share_of_step': ms_mlp / tot if tot else None}
         extra['profile_ms_per_step_eager'] = tot / a.profile_steps if tot else None
 

@@ -149,6 +149,10 @@ TDIFF_API int tdiff_scatter_mean3(const float* d_src, const int32_t* h_counts, i
 /* ---- instrumentation ------------------------------------------------------------------------------------
  * Number of kernel launches issued by this engine since creation (graph replays count their nodes). */
 TDIFF_API int64_t tdiff_launch_count(tdiff_engine* e);
+/* Edge-MLP execution mode of this engine (env TDIFF_EDGE_MLP at creation): 0 FP32 FFMA ("simt"), 2 tcgen05 bf16x2 split with keys in HBM
+ * ("tc3v2"), 3 tcgen05 bf16x3 split ("tc6"), 5 tcgen05 bf16x2 split, gaussian block on the tensor core and attention logits fused into the
+ * key-MLP epilogue (default, "tc3"). */
+TDIFF_API int tdiff_edge_mlp_mode(tdiff_engine* e);
 /* Time (ms, CUDA events on `stream`) and count of the attention-aggregate launches accumulated while profiling is on. */
 TDIFF_API int tdiff_profile(tdiff_engine* e, int enable);
 TDIFF_API int tdiff_profile_read(tdiff_engine* e, double* ms_aggregate_h, int64_t* n_aggregate_h, double* ms_aggregate_x,

@@ -145,6 +145,14 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -154,7 +162,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 // LayerNorm affine parameters travel as a kernel argument (constant bank: no L2 round trips in the row threads)
-struct LnParams { float g[128]; float b[128]; };
+struct LnParams { float g[128]; float b[128]; float b2[128]; };
 
 // 8 consecutive values -> two bf16 pieces (16 bytes each); residual of the first piece is exact in fp32
 __device__ __forceinline__ void split8_store(uint32_t addr_p0, uint32_t addr_p1, const float (&y)[8]) {
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, const unsigned char* __restrict__ etype,
                    const float* __restrict__ dist_arr, const int* __restrict__ row_nodes, long long n_rows, int k, TdMlp m,
                    const unsigned char* __restrict__ w2_image, const unsigned char* __restrict__ tab3_image, const float* __restrict__ offsets,
-                   float coeff, const float* __restrict__ tslow, float* __restrict__ out, int dbg, const __grid_constant__ LnParams lp, long long* __restrict__ ts) {
+                   float coeff, const float* __restrict__ tslow, const float* __restrict__ qnode, float* __restrict__ out, int dbg, const __grid_constant__ LnParams lp, long long* __restrict__ ts) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sW = sbase + oW, sA = sbase + oA, sS = sbase + oS, sG = sbase + oG, sT = sbase + oT, sX = sbase + oX, sBar = sbase + oBar;
@@ -272,16 +280,23 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       const uint32_t ph = (uint32_t)(it & 1);
       const bool valid = s0 >= 0;
       if (rwp == 0) stamp(0, it, 0);
-      // ---- x = P[dst, offA + 32*qq ..] (rows of a warp usually share the destination: broadcast loads)
-      f2 x[16];
+      // ---- P[dst, offA + 32*qq ..] (rows of a warp usually share the destination: broadcast loads) stays in flight while we wait
+      //      for the gathered source row in the staging tile (column atom qq); rare edge types add their precomputed gaussian block
+      float4 av[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && !(dbg & 4)) v = __ldg(reinterpret_cast<const float4*>(P + (size_t)d0 * TD_NPROJ + m.offA + 32 * qq + 4 * c));
-        x[2 * c] = pk2(v.x, v.y); x[2 * c + 1] = pk2(v.z, v.w);
+        av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && !(dbg & 4)) av[c] = __ldg(reinterpret_cast<const float4*>(P + (size_t)d0 * TD_NPROJ + m.offA + 32 * qq + 4 * c));
+      }
+      f2 x[16];
+      mbar_wait(bar(B_S_FULL), ph);
+      if (rwp == 0) stamp(0, it, 1);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = lds128(sS + (uint32_t)qq * kAtom + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4));
+        x[2 * c] = add2(pk2(v.x, v.y), pk2(av[c].x, av[c].y)); x[2 * c + 1] = add2(pk2(v.z, v.w), pk2(av[c].z, av[c].w));
       }
       if (valid && t0 != 3 && !(dbg & 8)) {
-        // rare edge types (every edge that touches a ligand atom): gaussian/type block precomputed by edge_slow_kernel, row-indexed
         const float* tr = tslow + (size_t)((blockIdx.x + it * (long long)gridDim.x) * 128 + r) * TD_H + 32 * qq;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -289,26 +304,23 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
           x[2 * c] = add2(x[2 * c], pk2(v.x, v.y)); x[2 * c + 1] = add2(x[2 * c + 1], pk2(v.z, v.w));
         }
       }
-      // ---- + the gathered source row from the staging tile (column atom qq)
-      mbar_wait(bar(B_S_FULL), ph);
-      if (rwp == 0) stamp(0, it, 1);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = lds128(sS + (uint32_t)qq * kAtom + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4));
-        x[2 * c] = add2(x[2 * c], pk2(v.x, v.y)); x[2 * c + 1] = add2(x[2 * c + 1], pk2(v.z, v.w));
-      }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_S_EMPTY));
       // ---- + gaussian/type block from the tensor core
       mbar_wait(bar(B_DPRE_FULL0 + (int)ph), (uint32_t)((it >> 1) & 1));
       if (rwp == 0) stamp(0, it, 2);
       tc_fence_after();
+      {
+        uint32_t v0[16], v1[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(32 * q) << 16) + 256u + ph * 128u + (uint32_t)(32 * qq);
+        tmem_ld16_nowait(ta, v0);
+        tmem_ld16_nowait(ta + 16u, v1);
+        tmem_ld_wait();
 #pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + 256u + ph * 128u + (uint32_t)(32 * qq + c0), v);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[c0 / 2 + i] = add2(x[c0 / 2 + i], pk2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])));
+        for (int i = 0; i < 8; ++i) {
+          x[i] = add2(x[i], pk2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1])));
+          x[8 + i] = add2(x[8 + i], pk2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1])));
+        }
       }
       tc_fence_before();
       // ---- gaussians of the NEXT tile now (the small MMA and its round trip overlap this tile's LayerNorm), metadata two ahead
@@ -462,7 +474,7 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
     }
   } else {
     // ================================================================= epilogue (warps 0..3 <-> TMEM lanes 32w..32w+31)
-    reg_dec<64>();
+    reg_inc<88>();     // register budget: 128*88 + 128*56 + 128*40 + 512*80 = 64512 = 896 threads x 72
     for (long long it = 0; it < my_tiles; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const uint32_t ph = (uint32_t)(it & 1), ph2 = (uint32_t)((it >> 1) & 1);
@@ -471,19 +483,59 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       if (warp == 0) stamp(3, it, 1);
       tc_fence_after();
       const long long idx = tile * 128 + warp * 32 + lane;
-      float* orow = out + (size_t)idx * 128;
+      if (qnode == nullptr) {
+        // ---- value MLPs: out[row, 0:128] = D + b2
+        float* orow = out + (size_t)idx * 128;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + ph * 128u + (uint32_t)c0, v);
-        if (idx < n_rows && !(dbg & 1)) {
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + ph * 128u + (uint32_t)c0, v);
+          if (idx < n_rows && !(dbg & 1)) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            const float4 ba = __ldg(reinterpret_cast<const float4*>(m.b2 + c0 + c)), bb = __ldg(reinterpret_cast<const float4*>(m.b2 + c0 + c + 4));
-            stg256(orow + c0 + c, __uint_as_float(v[c]) + ba.x, __uint_as_float(v[c + 1]) + ba.y, __uint_as_float(v[c + 2]) + ba.z,
-                   __uint_as_float(v[c + 3]) + ba.w, __uint_as_float(v[c + 4]) + bb.x, __uint_as_float(v[c + 5]) + bb.y,
-                   __uint_as_float(v[c + 6]) + bb.z, __uint_as_float(v[c + 7]) + bb.w);
+            for (int c = 0; c < 32; c += 8) {
+              const float* bb = lp.b2 + c0 + c;
+              stg256(orow + c0 + c, __uint_as_float(v[c]) + bb[0], __uint_as_float(v[c + 1]) + bb[1], __uint_as_float(v[c + 2]) + bb[2],
+                     __uint_as_float(v[c + 3]) + bb[3], __uint_as_float(v[c + 4]) + bb[4], __uint_as_float(v[c + 5]) + bb[5],
+                     __uint_as_float(v[c + 6]) + bb[6], __uint_as_float(v[c + 7]) + bb[7]);
+            }
           }
+        }
+      } else {
+        // ---- key MLPs: the keys never leave the SM.  out[row, 0:16] = attention logits  sum_d q[dst, 8h+d] * k[row, 8h+d] / sqrt(8)
+        //      (reference models/uni_transformer.py:73,135); thread = edge row, q row of the destination read as broadcast loads.
+        int dst = 0;
+        if (idx < n_rows) {
+          const unsigned a = (unsigned)idx / (unsigned)k;
+          dst = row_nodes ? row_nodes[a] : (int)a;
+        }
+        const float* qrow = qnode + (size_t)dst * TD_H;
+        float lg[16];
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          float4 qv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) qv[i] = __ldg(reinterpret_cast<const float4*>(qrow + c0 + 4 * i));
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + ph * 128u + (uint32_t)c0, v);
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            const float* bb = lp.b2 + c0 + 8 * hh;
+            const float4 qa = qv[2 * hh], qb = qv[2 * hh + 1];
+            float s = (__uint_as_float(v[8 * hh]) + bb[0]) * qa.x;
+            s = fmaf(__uint_as_float(v[8 * hh + 1]) + bb[1], qa.y, s);
+            s = fmaf(__uint_as_float(v[8 * hh + 2]) + bb[2], qa.z, s);
+            s = fmaf(__uint_as_float(v[8 * hh + 3]) + bb[3], qa.w, s);
+            s = fmaf(__uint_as_float(v[8 * hh + 4]) + bb[4], qb.x, s);
+            s = fmaf(__uint_as_float(v[8 * hh + 5]) + bb[5], qb.y, s);
+            s = fmaf(__uint_as_float(v[8 * hh + 6]) + bb[6], qb.z, s);
+            s = fmaf(__uint_as_float(v[8 * hh + 7]) + bb[7], qb.w, s);
+            lg[c0 / 8 + hh] = s * 0.35355339059327373f;          // 1/sqrt(8)
+          }
+        }
+        if (idx < n_rows && !(dbg & 1)) {
+          float* orow = out + (size_t)idx * TD_HEADS;
+          stg256(orow, lg[0], lg[1], lg[2], lg[3], lg[4], lg[5], lg[6], lg[7]);
+          stg256(orow + 8, lg[8], lg[9], lg[10], lg[11], lg[12], lg[13], lg[14], lg[15]);
         }
       }
       tc_fence_before();
@@ -543,11 +595,13 @@ edge_slow_kernel(const int* __restrict__ src, const unsigned char* __restrict__ 
 
 void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_rows,
                            int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
-                           const float* h_ln_g, const float* h_ln_b, float* tslow, float* out, int sm_count, cudaStream_t st) {
+                           const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const float* qnode, float* out, int sm_count,
+                           cudaStream_t st) {
   if (n_rows == 0) return;
   LnParams lp;
   memcpy(lp.g, h_ln_g, sizeof(lp.g));
   memcpy(lp.b, h_ln_b, sizeof(lp.b));
+  memcpy(lp.b2, h_b2, sizeof(lp.b2));
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(edge_mlp_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
@@ -567,7 +621,7 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
     dbg = e ? atoi(e) : 0;
     if (getenv("TDIFF_V3_TS")) { cudaMalloc(&d_ts, 16 * 4 * 8 * 8); cudaMemset(d_ts, 0, 16 * 4 * 8 * 8); }
   }
-  edge_mlp_v3_kernel<<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_rows, k, m, w2_image, tab3_image, offsets, coeff, tslow, out, dbg, lp, d_ts);
+  edge_mlp_v3_kernel<<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_rows, k, m, w2_image, tab3_image, offsets, coeff, tslow, qnode, out, dbg, lp, d_ts);
   if (d_ts && n_rows > 1000000) {          // dump the timeline of the first big launch, once
     static bool dumped = false;
     if (!dumped) {

@@ -538,11 +538,14 @@ struct Prof {
 };
 
 // per-edge MLP dispatch: tensor-core path for the 128-wide MLPs (hk, hv, xk), FFMA path for xv (16 outputs) or when forced
+// `qnode` != NULL (v3 path only): the MLP is a key MLP and `out` receives the 16 attention logits per row instead of the 128 keys
+bool fused_logits(const tdiff_engine* e) { return e->mlp_mode == 2 && e->mlp_v3; }
 void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
-              long long n_rows, int K, const TdMlp& m, const float* offsets, float coeff, float* out, cudaStream_t st) {
+              long long n_rows, int K, const TdMlp& m, const float* offsets, float coeff, float* out, cudaStream_t st,
+              const float* qnode = nullptr) {
   if (e->mlp_mode == 2 && e->mlp_v3 && m.nout == TD_H && m.w2_img && m.tab3_img)
     td_launch_edge_mlp_v3(P, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, m.tab3_img, offsets, coeff,
-                          e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena), e->tslow.as<float>(), out, e->sm_count, st);
+                          e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena), e->host_arena.data() + (m.b2 - e->arena), e->tslow.as<float>(), qnode, out, e->sm_count, st);
   else if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
     td_launch_edge_mlp_tc(P, xm, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, e->mlp_mode, offsets, coeff, out, e->sm_count, st);
   else
@@ -585,12 +588,14 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     if (e->mlp_mode != 0) { td_launch_edge_geom(xm[cur], src, N, K, e->dist.as<float>(), st); e->launches += 1; }
     {
       Prof pr(e, st, EV_EDGE_MLP);
-      edge_mlp(e, P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st);
+      edge_mlp(e, P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st,
+               fused_logits(e) ? q : nullptr);
       edge_mlp(e, P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), st);
     }
     {
       Prof pr(e, st, EV_AGG_H);
-      td_launch_aggregate_h(e->kbuf.as<float>(), e->vbuf.as<float>(), e->e_w.as<float>(), src, q, h, h, N, K, st);
+      if (fused_logits(e)) td_launch_aggregate_h_logits(e->kbuf.as<float>(), e->vbuf.as<float>(), e->e_w.as<float>(), src, h, h, N, K, st);
+      else td_launch_aggregate_h(e->kbuf.as<float>(), e->vbuf.as<float>(), e->e_w.as<float>(), src, q, h, h, N, K, st);
     }
     e->launches += 5;
     if (fix_x || Nl == 0) continue;     // h2x only moves ligand atoms; with fix_x its result is discarded (:204-206)
@@ -598,12 +603,16 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     node_side(e, h, N, ly.h2x, P, q, st);
     {
       Prof pr(e, st, EV_EDGE_MLP);
-      edge_mlp(e, P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st);
+      edge_mlp(e, P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st,
+               fused_logits(e) ? q : nullptr);
       edge_mlp(e, P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.v, ly.offsets, ly.coeff, e->v16.as<float>(), st);
     }
     {
       Prof pr(e, st, EV_AGG_X);
-      td_launch_aggregate_x(e->kbuf.as<float>(), e->v16.as<float>(), e->e_w.as<float>(), src, q, xm[cur], e->lig_node.as<int>(), xm[cur ^ 1], Nl, K, st);
+      if (fused_logits(e))
+        td_launch_aggregate_x_logits(e->kbuf.as<float>(), e->v16.as<float>(), e->e_w.as<float>(), src, xm[cur], e->lig_node.as<int>(), xm[cur ^ 1], Nl, K, st);
+      else
+        td_launch_aggregate_x(e->kbuf.as<float>(), e->v16.as<float>(), e->e_w.as<float>(), src, q, xm[cur], e->lig_node.as<int>(), xm[cur ^ 1], Nl, K, st);
     }
     e->launches += 5;
     cur ^= 1;
@@ -890,6 +899,7 @@ extern "C" int tdiff_scatter_mean3(const float* d_src, const int32_t* h_counts, 
 
 // ---------------------------------------------------------------------------------------------- instrumentation
 extern "C" int64_t tdiff_launch_count(tdiff_engine* e) { return e ? e->launches : 0; }
+extern "C" int tdiff_edge_mlp_mode(tdiff_engine* e) { return !e ? TDIFF_EINVAL : (e->mlp_mode == 2 && e->mlp_v3) ? 5 : e->mlp_mode; }
 
 extern "C" int tdiff_profile(tdiff_engine* e, int enable) {
   if (!e) return set_err(TDIFF_EINVAL, "null engine");

@@ -128,12 +128,17 @@ void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, con
                            float* out, int sm_count, cudaStream_t st);
 void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_rows,
                            int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
-                           const float* h_ln_g, const float* h_ln_b, float* tslow, float* out, int sm_count, cudaStream_t st);
+                           const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const float* qnode, float* out, int sm_count,
+                           cudaStream_t st);
 void td_launch_rows_tc(int mode, const float* in, int ldi, int in_off, long long n_rows, TdMlp m, const unsigned char* w_image, int pieces, float* out,
                        int ldo, int nblocks, int sm_count, cudaStream_t st);
 void td_launch_aggregate_h(const float* kbuf, const float* vbuf, const float* e_w, const int* src, const float* q, const float* h_in,
                            float* h_out, int n_nodes, int k, cudaStream_t st);
 void td_launch_aggregate_x(const float* kbuf, const float* v16, const float* e_w, const int* src, const float* q, const float4* xm_in,
                            const int* row_nodes, float4* xm_out, int n_rows, int k, cudaStream_t st);
+void td_launch_aggregate_h_logits(const float* logits, const float* vbuf, const float* e_w, const int* src, const float* h_in, float* h_out,
+                                  int n_nodes, int k, cudaStream_t st);
+void td_launch_aggregate_x_logits(const float* logits, const float* v16, const float* e_w, const int* src, const float4* xm_in,
+                                  const int* row_nodes, float4* xm_out, int n_rows, int k, cudaStream_t st);
 void td_launch_head(const float* h, const int* lig_node, int n_lig, const float* w1t, const float* b1, const float* w2, const float* b2,
                     int n_classes, float* logits, cudaStream_t st);

@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(EC_WARPS * 32)
 edge_const_kernel(const float4* __restrict__ xm, const int* __restrict__ src, long long n_slots, int k,
                   const float* __restrict__ offsets, float coeff, const float* __restrict__ w1t, const float* __restrict__ b1,
                   const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ w2, float b2,
-                  unsigned char* __restrict__ etype, float* __restrict__ e_w) {
+                  unsigned char* __restrict__ etype, float* __restrict__ e_w, int* __restrict__ slow_list, int* __restrict__ n_slow) {
   __shared__ float s_w1t[TD_NG * TD_H];
   __shared__ float s_b1[TD_H], s_g[TD_H], s_b[TD_H], s_w2[TD_H];
   for (int i = threadIdx.x; i < TD_NG * TD_H; i += blockDim.x) s_w1t[i] = w1t[i];
@@ -50,21 +50,25 @@ edge_const_kernel(const float4* __restrict__ xm, const int* __restrict__ src, lo
     acc = warp_sum(acc) + b2;
     if (lane == 0) {
       const bool ns = xs.w != 0.0f, nd = xd.w != 0.0f;
-      etype[e] = ns ? (nd ? 0 : 1) : (nd ? 2 : 3);
+      const int ty = ns ? (nd ? 0 : 1) : (nd ? 2 : 3);
+      etype[e] = (unsigned char)ty;
       e_w[e] = 1.0f / (1.0f + expf(-acc));
+      // every edge that touches a ligand atom (type != 3): compact list for edge_slow_kernel (order is irrelevant)
+      if (ty != 3 && slow_list) slow_list[atomicAdd(n_slow, 1)] = (int)e;
     }
   }
 }
 
 void td_launch_edge_const(const float4* xm, const int* src, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
-                          unsigned char* etype, float* e_w, cudaStream_t st) {
+                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, cudaStream_t st) {
   long long n_slots = (long long)n_nodes * k;
   if (n_slots == 0) return;
   long long blocks = (n_slots + EC_WARPS * 4 - 1) / (EC_WARPS * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
+  if (n_slow) cudaMemsetAsync(n_slow, 0, sizeof(int), st);
   edge_const_kernel<<<(int)blocks, EC_WARPS * 32, 0, st>>>(xm, src, n_slots, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2,
-                                                            etype, e_w);
+                                                            etype, e_w, slow_list, n_slow);
 }
 
 // Per-layer edge length |x_dst - x_src| (reference models/uni_transformer.py:188-189) for every slot, from the layer's input

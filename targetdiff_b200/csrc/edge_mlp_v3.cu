@@ -181,6 +181,8 @@ __device__ __forceinline__ void split8_store(uint32_t addr_p0, uint32_t addr_p1,
 
 using namespace v3;
 
+// NOUT = 128: key / value MLPs (hk, hv, xk);  NOUT = 16: the per-head scalar value MLP of h2x (xv)
+template <int NOUT>
 __global__ void __launch_bounds__(kThreads, 1)
 edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, const unsigned char* __restrict__ etype,
                    const float* __restrict__ dist_arr, const int* __restrict__ row_nodes, long long n_rows, int k, TdMlp m,
@@ -199,7 +201,10 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
 
   if ((sbase & 1023u) != 0) __trap();            // SWIZZLE_128B atoms need a 1024-byte aligned window
   // ---- one-time setup: weight images -> smem, barriers, TMEM
-  for (int i = tid; i < 2 * kPiece / 16; i += kThreads) {
+  constexpr int kWAtom = NOUT * 128;            // one K-half of a weight piece: NOUT rows x 128 B
+  constexpr int kWPiece = 2 * kWAtom;
+  constexpr uint32_t kIdescMain = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
+  for (int i = tid; i < 2 * kWPiece / 16; i += kThreads) {
     const uint4 v = reinterpret_cast<const uint4*>(w2_image)[i];
     sts128(sW + 16 * i, v.x, v.y, v.z, v.w);
   }
@@ -461,8 +466,8 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
           const int pa_ = (term == 2) ? 1 : 0, pb_ = (term == 1) ? 1 : 0;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t koff = (kk >> 2) * kAtom + (kk & 3) * 32;
-            umma_bf16(d_addr, desc_sw128(sA + pa_ * kPiece + koff), desc_sw128(sW + pb_ * kPiece + koff), kIdesc, accum);
+            const uint32_t koff = (kk >> 2) * kAtom + (kk & 3) * 32, woff = (kk >> 2) * kWAtom + (kk & 3) * 32;
+            umma_bf16(d_addr, desc_sw128(sA + pa_ * kPiece + koff), desc_sw128(sW + pb_ * kWPiece + woff), kIdescMain, accum);
             accum = 1;
           }
         }
@@ -483,7 +488,20 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       if (warp == 0) stamp(3, it, 1);
       tc_fence_after();
       const long long idx = tile * 128 + warp * 32 + lane;
-      if (qnode == nullptr) {
+      if (NOUT == 16) {
+        // ---- xv: out[row, 0:16] = D[:, 0:16] + b2
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + ph * 128u, v);
+        if (idx < n_rows && !(dbg & 1)) {
+          float* orow = out + (size_t)idx * 16;
+          stg256(orow, __uint_as_float(v[0]) + lp.b2[0], __uint_as_float(v[1]) + lp.b2[1], __uint_as_float(v[2]) + lp.b2[2],
+                 __uint_as_float(v[3]) + lp.b2[3], __uint_as_float(v[4]) + lp.b2[4], __uint_as_float(v[5]) + lp.b2[5],
+                 __uint_as_float(v[6]) + lp.b2[6], __uint_as_float(v[7]) + lp.b2[7]);
+          stg256(orow + 8, __uint_as_float(v[8]) + lp.b2[8], __uint_as_float(v[9]) + lp.b2[9], __uint_as_float(v[10]) + lp.b2[10],
+                 __uint_as_float(v[11]) + lp.b2[11], __uint_as_float(v[12]) + lp.b2[12], __uint_as_float(v[13]) + lp.b2[13],
+                 __uint_as_float(v[14]) + lp.b2[14], __uint_as_float(v[15]) + lp.b2[15]);
+        }
+      } else if (qnode == nullptr) {
         // ---- value MLPs: out[row, 0:128] = D + b2
         float* orow = out + (size_t)idx * 128;
 #pragma unroll 1
@@ -555,64 +573,68 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
 
 // Pre-pass for the rare edge types: tslow[row] = tab[type][20] + sum_j g_j(dist) * tab[type][j] for rows with type != 3 (6-7 % of the
 // rows: every edge that touches a ligand atom).  Row-indexed buffer, only those rows are written.  No shared memory is used, so the
-// 43 KB table stays L1-resident.  One warp per chunk of 32 rows; lanes 0..19 evaluate the gaussians of the row being processed.
+// 43 KB table stays L1-resident.  One warp per such row; lanes 0..19 evaluate its gaussians.
+//   slow_list != NULL: rows are slots (x2h launches); the list of type != 3 slots was compacted by edge_const_kernel.
+//   slow_list == NULL: scan all n_rows rows of a destination subset (h2x launches: ligand destinations, every row is of type 0 / 2).
 __global__ void __launch_bounds__(256)
 edge_slow_kernel(const int* __restrict__ src, const unsigned char* __restrict__ etype, const float* __restrict__ dist_arr,
-                 const int* __restrict__ row_nodes, long long n_rows, int k, const float* __restrict__ tab, const float* __restrict__ offsets,
-                 float coeff, float* __restrict__ tslow) {
+                 const int* __restrict__ row_nodes, long long n_rows, int k, const int* __restrict__ slow_list, const int* __restrict__ n_slow,
+                 const float* __restrict__ tab, const float* __restrict__ offsets, float coeff, float* __restrict__ tslow) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * 8;
   const float mu = offsets[lane < TD_NG ? lane : 0];
-  for (long long chunk = warp0; chunk * 32 < n_rows; chunk += nwarps) {
-    const long long idx = chunk * 32 + lane;
-    int s = -1, ty = 3;
-    float dist = 0.f;
-    if (idx < n_rows) {
-      const unsigned a = (unsigned)idx / (unsigned)k;
-      const int j = (int)((unsigned)idx - a * (unsigned)k);
-      const int dst = row_nodes ? row_nodes[a] : (int)a;
-      const size_t e = (size_t)dst * k + j;
-      s = src[e]; ty = etype[e]; dist = dist_arr[e];
+  const long long n_items = slow_list ? (long long)*n_slow : n_rows;
+  for (long long i = warp0; i < n_items; i += nwarps) {
+    long long row;
+    size_t e;
+    if (slow_list) {
+      e = (size_t)slow_list[i];
+      row = (long long)e;
+    } else {
+      row = i;
+      const unsigned a = (unsigned)row / (unsigned)k;
+      e = (size_t)row_nodes[a] * k + (row - (long long)a * k);
     }
-    for (unsigned mask = __ballot_sync(0xffffffffu, s >= 0 && ty != 3); mask; mask &= mask - 1) {
-      const int rr = __ffs(mask) - 1;
-      const int tr = __shfl_sync(0xffffffffu, ty, rr);
-      const float dd = __shfl_sync(0xffffffffu, dist, rr);
-      const float tmu = dd - mu;
-      const float gj = expf(coeff * (tmu * tmu));
-      const float* tb = tab + (size_t)tr * TD_TAB * TD_H + 4 * lane;
-      float4 v = __ldg(reinterpret_cast<const float4*>(tb + TD_NG * TD_H));
+    const int ty = etype[e];
+    if (src[e] < 0 || ty == 3) continue;
+    const float tmu = dist_arr[e] - mu;
+    const float gj = expf(coeff * (tmu * tmu));
+    const float* tb = tab + (size_t)ty * TD_TAB * TD_H + 4 * lane;
+    float4 v = __ldg(reinterpret_cast<const float4*>(tb + TD_NG * TD_H));
 #pragma unroll 5
-      for (int jj = 0; jj < TD_NG; ++jj) {
-        const float g = __shfl_sync(0xffffffffu, gj, jj);
-        const float4 cj = __ldg(reinterpret_cast<const float4*>(tb + jj * TD_H));
-        v.x = fmaf(g, cj.x, v.x); v.y = fmaf(g, cj.y, v.y); v.z = fmaf(g, cj.z, v.z); v.w = fmaf(g, cj.w, v.w);
-      }
-      *reinterpret_cast<float4*>(tslow + (size_t)(chunk * 32 + rr) * TD_H + 4 * lane) = v;
+    for (int jj = 0; jj < TD_NG; ++jj) {
+      const float g = __shfl_sync(0xffffffffu, gj, jj);
+      const float4 cj = __ldg(reinterpret_cast<const float4*>(tb + jj * TD_H));
+      v.x = fmaf(g, cj.x, v.x); v.y = fmaf(g, cj.y, v.y); v.z = fmaf(g, cj.z, v.z); v.w = fmaf(g, cj.w, v.w);
     }
+    *reinterpret_cast<float4*>(tslow + (size_t)row * TD_H + 4 * lane) = v;
   }
 }
 
 void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_rows,
                            int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
-                           const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const float* qnode, float* out, int sm_count,
-                           cudaStream_t st) {
+                           const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const int* slow_list, const int* n_slow,
+                           const float* qnode, float* out, int sm_count, cudaStream_t st) {
   if (n_rows == 0) return;
   LnParams lp;
   memcpy(lp.g, h_ln_g, sizeof(lp.g));
   memcpy(lp.b, h_ln_b, sizeof(lp.b));
-  memcpy(lp.b2, h_b2, sizeof(lp.b2));
+  memset(lp.b2, 0, sizeof(lp.b2));
+  memcpy(lp.b2, h_b2, sizeof(float) * (size_t)m.nout);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(edge_mlp_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(edge_mlp_v3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(edge_mlp_v3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     configured = true;
   }
   const long long n_tiles = (n_rows + 127) / 128;
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
   {
-    long long chunks = (n_rows + 31) / 32, blocks = (chunks + 7) / 8;
+    const bool listed = (row_nodes == nullptr) && slow_list;            // x2h: iterate the compacted list; h2x: scan the (few) rows
+    long long blocks = listed ? sm_count * 8 : (n_rows + 7) / 8;
     if (blocks > sm_count * 8) blocks = sm_count * 8;
-    edge_slow_kernel<<<(int)blocks, 256, 0, st>>>(src, etype, dist, row_nodes, n_rows, k, m.tab, offsets, coeff, tslow);
+    edge_slow_kernel<<<(int)blocks, 256, 0, st>>>(src, etype, dist, row_nodes, n_rows, k, listed ? slow_list : nullptr, n_slow, m.tab, offsets,
+                                                  coeff, tslow);
   }
   static int dbg = -1;
   static long long* d_ts = nullptr;
@@ -621,7 +643,12 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
     dbg = e ? atoi(e) : 0;
     if (getenv("TDIFF_V3_TS")) { cudaMalloc(&d_ts, 16 * 4 * 8 * 8); cudaMemset(d_ts, 0, 16 * 4 * 8 * 8); }
   }
-  edge_mlp_v3_kernel<<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_rows, k, m, w2_image, tab3_image, offsets, coeff, tslow, qnode, out, dbg, lp, d_ts);
+  if (m.nout == 16)
+    edge_mlp_v3_kernel<16><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_rows, k, m, w2_image, tab3_image, offsets, coeff, tslow,
+                                                         nullptr, out, dbg, lp, d_ts);
+  else
+    edge_mlp_v3_kernel<128><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_rows, k, m, w2_image, tab3_image, offsets, coeff, tslow,
+                                                          qnode, out, dbg, lp, d_ts);
   if (d_ts && n_rows > 1000000) {          // dump the timeline of the first big launch, once
     static bool dumped = false;
     if (!dumped) {

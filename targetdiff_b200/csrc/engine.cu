@@ -75,7 +75,7 @@ struct tdiff_engine {
   bool bound = false, has_ligand = false, have_graph = false;
   int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
   DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
-  DevBuf xm0, xm1, offset, h0, h, P, q, src, etype, e_w, dist, tslow, kbuf, vbuf, v16, lig_pos, lig_v, logits;
+  DevBuf xm0, xm1, offset, h0, h, P, q, src, etype, e_w, dist, tslow, slow_list, n_slow, kbuf, vbuf, v16, lig_pos, lig_v, logits;
   DevBuf step, err_flag, node_off, total_edges;
   DevBuf stage[8];   // staging for tdiff_sample_host
   // ---- instrumentation
@@ -123,15 +123,15 @@ inline float bf16_f(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcp
 
 // W2 [128 out (N), 128 in (K)] -> three bf16 pieces (w = w1 + w2 + w3), each stored as the shared-memory image the UMMA
 // descriptor of edge_mlp_tc.cu expects: K-major, SWIZZLE_128B, two K-halves of [128 rows x 128 B], 16-byte chunks XOR row%8.
-void pack_umma_image(const float* w2, std::vector<unsigned char>& img, size_t off) {
-  for (int n = 0; n < 128; ++n)
+void pack_umma_image(const float* w2, std::vector<unsigned char>& img, size_t off, int nrows = 128) {
+  for (int n = 0; n < nrows; ++n)
     for (int kk = 0; kk < 128; ++kk) {
       float r = w2[(size_t)n * 128 + kk];
-      const size_t o = (size_t)(kk / 64) * 16384 + (size_t)n * 128 + (size_t)((((kk % 64) / 8) ^ (n & 7)) * 16) + (size_t)(kk % 8) * 2;
+      const size_t o = (size_t)(kk / 64) * ((size_t)nrows * 128) + (size_t)n * 128 + (size_t)((((kk % 64) / 8) ^ (n & 7)) * 16) + (size_t)(kk % 8) * 2;
       for (int p = 0; p < 3; ++p) {
         const uint16_t b = bf16_rn(r);
         r = r - bf16_f(b);
-        memcpy(&img[off + (size_t)p * 32768 + o], &b, 2);
+        memcpy(&img[off + (size_t)p * ((size_t)nrows * 256) + o], &b, 2);
       }
     }
 }
@@ -179,10 +179,10 @@ bool pack_edge_mlp(Packer& pk, const std::string& p, int nout, MlpOff& o, const 
     for (int n = 0; n < nout; ++n) pk.host[o.w2t + (size_t)kk * nout + n] = w2[(size_t)n * TD_H + kk];
   o.b2 = pk.alloc(nout); memcpy(&pk.host[o.b2], b2, nout * sizeof(float));
   o.img = -1; o.tab3 = -1;
-  if (nout == TD_H) {
+  if (nout == TD_H || nout == 16) {
     o.img = (long long)pk.img.size();
-    pk.img.resize(pk.img.size() + 3 * 32768, 0);
-    pack_umma_image(w2, pk.img, (size_t)o.img);
+    pk.img.resize(pk.img.size() + 3 * (size_t)nout * 256, 0);
+    pack_umma_image(w2, pk.img, (size_t)o.img, nout);
     o.tab3 = (long long)pk.img.size();
     pk.img.resize(pk.img.size() + 3 * 8192, 0);
     pack_tab3_image(&pk.host[o.tab + (size_t)3 * TD_TAB * TD_H], pk.img, (size_t)o.tab3);
@@ -408,7 +408,7 @@ extern "C" void tdiff_destroy(tdiff_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   DevBuf* bufs[] = {&e->node_ptr, &e->prot_ptr, &e->prot_node, &e->prot_graph, &e->lig_node, &e->lig_graph, &e->node_lig, &e->xm0, &e->xm1,
-                    &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
+                    &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->slow_list, &e->n_slow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
                     &e->lig_v, &e->logits, &e->step, &e->err_flag, &e->node_off, &e->total_edges};
   for (auto* b : bufs) b->release();
   for (auto& b : e->stage) b.release();
@@ -454,7 +454,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   bad |= e->xm0.ensure(N * 16) | e->xm1.ensure(N * 16) | e->offset.ensure((size_t)B * 16);
   bad |= e->h0.ensure(N * TD_H * 4) | e->h.ensure(N * TD_H * 4) | e->P.ensure((size_t)N * TD_NPROJ * 4) | e->q.ensure(N * TD_H * 4);
   bad |= e->src.ensure(slots * 4) | e->etype.ensure(slots) | e->e_w.ensure(slots * 4) | e->dist.ensure(slots * 4);
-  if (e->mlp_mode == 2 && e->mlp_v3) bad |= e->tslow.ensure(slots * TD_H * 4);   // row-indexed, only ligand-touching rows are touched
+  if (e->mlp_mode == 2 && e->mlp_v3) bad |= e->tslow.ensure(slots * TD_H * 4) | e->slow_list.ensure(slots * 4) | e->n_slow.ensure(16);   // row-indexed, only ligand-touching rows are touched
   bad |= e->kbuf.ensure(slots * TD_H * 4) | e->vbuf.ensure(slots * TD_H * 4) | e->v16.ensure((size_t)Nl * K * TD_HEADS * 4 + 16);
   bad |= e->lig_pos.ensure(Nl * 16 + 16) | e->lig_v.ensure(Nl * 4 + 4) | e->logits.ensure((size_t)Nl * e->cfg.num_classes * 4 + 4);
   bad |= e->node_off.ensure(N * 8);
@@ -543,9 +543,9 @@ bool fused_logits(const tdiff_engine* e) { return e->mlp_mode == 2 && e->mlp_v3;
 void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
               long long n_rows, int K, const TdMlp& m, const float* offsets, float coeff, float* out, cudaStream_t st,
               const float* qnode = nullptr) {
-  if (e->mlp_mode == 2 && e->mlp_v3 && m.nout == TD_H && m.w2_img && m.tab3_img)
+  if (e->mlp_mode == 2 && e->mlp_v3 && m.w2_img && m.tab3_img)
     td_launch_edge_mlp_v3(P, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, m.tab3_img, offsets, coeff,
-                          e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena), e->host_arena.data() + (m.b2 - e->arena), e->tslow.as<float>(), qnode, out, e->sm_count, st);
+                          e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena), e->host_arena.data() + (m.b2 - e->arena), e->tslow.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), qnode, out, e->sm_count, st);
   else if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
     td_launch_edge_mlp_tc(P, xm, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, e->mlp_mode, offsets, coeff, out, e->sm_count, st);
   else
@@ -578,7 +578,7 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
   td_launch_init_h(e->h0.as<float>(), xm[0], e->lig_v.as<int>(), e->node_lig.as<int>(), e->wl_t, e->bl, N, h, st);
   td_launch_knn(xm[0], e->node_ptr.as<int>(), e->B, e->max_ng, K, e->src.as<int>(), st);
   td_launch_edge_const(xm[0], src, N, K, e->ew_off, e->ew_coeff, e->ew_w1t, e->ew_b1, e->ew_g, e->ew_b, e->ew_w2, e->ew_b2,
-                       e->etype.as<unsigned char>(), e->e_w.as<float>(), st);
+                       e->etype.as<unsigned char>(), e->e_w.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), st);
   e->launches += 4;
   int cur = 0;
   for (size_t l = 0; l < e->layers.size(); ++l) {

@@ -113,7 +113,7 @@ __device__ __forceinline__ void tile_gemm_128(const float* __restrict__ As, cons
 void td_launch_knn(const float4* xm, const int* node_ptr, int n_graphs, int max_nodes_per_graph, int k, int* src, cudaStream_t st);
 void td_launch_edge_const(const float4* xm, const int* src, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
-                          unsigned char* etype, float* e_w, cudaStream_t st);
+                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, cudaStream_t st);
 void td_launch_protein_embed(const float* feat, int n_protein, int fdim, const float* w, const float* b, const int* prot_node,
                              float* h0, cudaStream_t st);
 void td_launch_init_h(const float* h0, const float4* xm, const int* lig_v, const int* node_lig, const float* wl_t, const float* bl,
@@ -128,8 +128,8 @@ void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, con
                            float* out, int sm_count, cudaStream_t st);
 void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_rows,
                            int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
-                           const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const float* qnode, float* out, int sm_count,
-                           cudaStream_t st);
+                           const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const int* slow_list, const int* n_slow,
+                           const float* qnode, float* out, int sm_count, cudaStream_t st);
 void td_launch_rows_tc(int mode, const float* in, int ldi, int in_off, long long n_rows, TdMlp m, const unsigned char* w_image, int pieces, float* out,
                        int ldo, int nblocks, int sm_count, cudaStream_t st);
 void td_launch_aggregate_h(const float* kbuf, const float* vbuf, const float* e_w, const int* src, const float* q, const float* h_in,

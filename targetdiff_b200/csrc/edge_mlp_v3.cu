@@ -584,30 +584,42 @@ edge_slow_kernel(const int* __restrict__ src, const unsigned char* __restrict__ 
   const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * 8;
   const float mu = offsets[lane < TD_NG ? lane : 0];
   const long long n_items = slow_list ? (long long)*n_slow : n_rows;
-  for (long long i = warp0; i < n_items; i += nwarps) {
-    long long row;
-    size_t e;
-    if (slow_list) {
-      e = (size_t)slow_list[i];
-      row = (long long)e;
-    } else {
-      row = i;
-      const unsigned a = (unsigned)row / (unsigned)k;
-      e = (size_t)row_nodes[a] * k + (row - (long long)a * k);
+  // 32 items per warp iteration: every lane fetches the metadata of one row (one latency for 32 rows), rows are then processed in turn
+  for (long long i0 = warp0 * 32; i0 < n_items; i0 += nwarps * 32) {
+    const long long i = i0 + lane;
+    long long row = -1;
+    int ty = 3;
+    float dist = 0.f;
+    if (i < n_items) {
+      size_t e;
+      if (slow_list) {
+        e = (size_t)slow_list[i];
+        row = (long long)e;
+      } else {
+        row = i;
+        const unsigned a = (unsigned)row / (unsigned)k;
+        e = (size_t)row_nodes[a] * k + (row - (long long)a * k);
+      }
+      ty = etype[e];
+      dist = dist_arr[e];
+      if (src[e] < 0 || ty == 3) row = -1;
     }
-    const int ty = etype[e];
-    if (src[e] < 0 || ty == 3) continue;
-    const float tmu = dist_arr[e] - mu;
-    const float gj = expf(coeff * (tmu * tmu));
-    const float* tb = tab + (size_t)ty * TD_TAB * TD_H + 4 * lane;
-    float4 v = __ldg(reinterpret_cast<const float4*>(tb + TD_NG * TD_H));
+    for (unsigned mask = __ballot_sync(0xffffffffu, row >= 0); mask; mask &= mask - 1) {
+      const int rr = __ffs(mask) - 1;
+      const long long rrow = __shfl_sync(0xffffffffu, row, rr);
+      const int tr = __shfl_sync(0xffffffffu, ty, rr);
+      const float tmu = __shfl_sync(0xffffffffu, dist, rr) - mu;
+      const float gj = expf(coeff * (tmu * tmu));
+      const float* tb = tab + (size_t)tr * TD_TAB * TD_H + 4 * lane;
+      float4 v = __ldg(reinterpret_cast<const float4*>(tb + TD_NG * TD_H));
 #pragma unroll 5
-    for (int jj = 0; jj < TD_NG; ++jj) {
-      const float g = __shfl_sync(0xffffffffu, gj, jj);
-      const float4 cj = __ldg(reinterpret_cast<const float4*>(tb + jj * TD_H));
-      v.x = fmaf(g, cj.x, v.x); v.y = fmaf(g, cj.y, v.y); v.z = fmaf(g, cj.z, v.z); v.w = fmaf(g, cj.w, v.w);
+      for (int jj = 0; jj < TD_NG; ++jj) {
+        const float g = __shfl_sync(0xffffffffu, gj, jj);
+        const float4 cj = __ldg(reinterpret_cast<const float4*>(tb + jj * TD_H));
+        v.x = fmaf(g, cj.x, v.x); v.y = fmaf(g, cj.y, v.y); v.z = fmaf(g, cj.z, v.z); v.w = fmaf(g, cj.w, v.w);
+      }
+      *reinterpret_cast<float4*>(tslow + (size_t)rrow * TD_H + 4 * lane) = v;
     }
-    *reinterpret_cast<float4*>(tslow + (size_t)row * TD_H + 4 * lane) = v;
   }
 }
 

@@ -73,9 +73,10 @@ struct tdiff_engine {
   const float *t_c0 = nullptr, *t_ct = nullptr, *t_logvar = nullptr, *t_la = nullptr, *t_l1ma = nullptr, *t_lca = nullptr, *t_l1mca = nullptr;
   // ---- batch
   bool bound = false, has_ligand = false, have_graph = false;
+  bool have_prev = false;               // src_prev / etype / e_w hold the previous forward's graph of this batch (edge_const reuse)
   int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
   DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
-  DevBuf xm0, xm1, offset, h0, h, P, q, src, etype, e_w, dist, tslow, slow_list, n_slow, kbuf, vbuf, v16, lig_pos, lig_v, logits;
+  DevBuf xm0, xm1, offset, h0, h, P, q, src, src_prev, etype, e_w, dist, tslow, slow_list, n_slow, kbuf, vbuf, v16, lig_pos, lig_v, logits;
   DevBuf step, err_flag, node_off, total_edges;
   DevBuf stage[8];   // staging for tdiff_sample_host
   // ---- instrumentation
@@ -408,7 +409,7 @@ extern "C" void tdiff_destroy(tdiff_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   DevBuf* bufs[] = {&e->node_ptr, &e->prot_ptr, &e->prot_node, &e->prot_graph, &e->lig_node, &e->lig_graph, &e->node_lig, &e->xm0, &e->xm1,
-                    &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->slow_list, &e->n_slow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
+                    &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->src_prev, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->slow_list, &e->n_slow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
                     &e->lig_v, &e->logits, &e->step, &e->err_flag, &e->node_off, &e->total_edges};
   for (auto* b : bufs) b->release();
   for (auto& b : e->stage) b.release();
@@ -445,7 +446,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
     for (int i = 0; i < lc[g]; ++i) { lig_node[a] = n; lig_graph[a] = g; node_lig[n] = a; ++a; ++n; }
   }
   node_ptr[B] = n; prot_ptr[B] = p;
-  e->bound = false; e->has_ligand = false; e->have_graph = false;
+  e->bound = false; e->has_ligand = false; e->have_graph = false; e->have_prev = false;
   e->B = B; e->N = (int)N; e->Np = (int)Np; e->Nl = (int)Nl; e->max_ng = max_ng;
   const size_t slots = (size_t)N * K;
   int bad = 0;
@@ -453,7 +454,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   bad |= e->lig_node.ensure(Nl * 4 + 4) | e->lig_graph.ensure(Nl * 4 + 4) | e->node_lig.ensure(N * 4);
   bad |= e->xm0.ensure(N * 16) | e->xm1.ensure(N * 16) | e->offset.ensure((size_t)B * 16);
   bad |= e->h0.ensure(N * TD_H * 4) | e->h.ensure(N * TD_H * 4) | e->P.ensure((size_t)N * TD_NPROJ * 4) | e->q.ensure(N * TD_H * 4);
-  bad |= e->src.ensure(slots * 4) | e->etype.ensure(slots) | e->e_w.ensure(slots * 4) | e->dist.ensure(slots * 4);
+  bad |= e->src.ensure(slots * 4) | e->src_prev.ensure(slots * 4) | e->etype.ensure(slots) | e->e_w.ensure(slots * 4) | e->dist.ensure(slots * 4);
   if (e->mlp_mode == 2 && e->mlp_v3) bad |= e->tslow.ensure(slots * TD_H * 4) | e->slow_list.ensure(slots * 4) | e->n_slow.ensure(16);   // row-indexed, only ligand-touching rows are touched
   bad |= e->kbuf.ensure(slots * TD_H * 4) | e->vbuf.ensure(slots * TD_H * 4) | e->v16.ensure((size_t)Nl * K * TD_HEADS * 4 + 16);
   bad |= e->lig_pos.ensure(Nl * 16 + 16) | e->lig_v.ensure(Nl * 4 + 4) | e->logits.ensure((size_t)Nl * e->cfg.num_classes * 4 + 4);
@@ -577,7 +578,7 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
   td_launch_scatter_ligand_pos(e->lig_pos.as<float4>(), e->lig_node.as<int>(), Nl, xm[0], st);
   td_launch_init_h(e->h0.as<float>(), xm[0], e->lig_v.as<int>(), e->node_lig.as<int>(), e->wl_t, e->bl, N, h, st);
   td_launch_knn(xm[0], e->node_ptr.as<int>(), e->B, e->max_ng, K, e->src.as<int>(), st);
-  td_launch_edge_const(xm[0], src, N, K, e->ew_off, e->ew_coeff, e->ew_w1t, e->ew_b1, e->ew_g, e->ew_b, e->ew_w2, e->ew_b2,
+  td_launch_edge_const(xm[0], src, e->src_prev.as<int>(), e->have_prev ? 1 : 0, N, K, e->ew_off, e->ew_coeff, e->ew_w1t, e->ew_b1, e->ew_g, e->ew_b, e->ew_w2, e->ew_b2,
                        e->etype.as<unsigned char>(), e->e_w.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), st);
   e->launches += 4;
   int cur = 0;
@@ -621,6 +622,7 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
   e->launches += 1;
   e->final_buf = cur;
   e->have_graph = true;
+  e->have_prev = true;
 }
 }  // namespace
 

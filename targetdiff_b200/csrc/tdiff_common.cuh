@@ -111,7 +111,7 @@ __device__ __forceinline__ void tile_gemm_128(const float* __restrict__ As, cons
 
 // Launchers (defined in the .cu files, called by engine.cu).  All asynchronous on `st`.
 void td_launch_knn(const float4* xm, const int* node_ptr, int n_graphs, int max_nodes_per_graph, int k, int* src, cudaStream_t st);
-void td_launch_edge_const(const float4* xm, const int* src, int n_nodes, int k, const float* offsets, float coeff,
+void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int have_prev, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
                           unsigned char* etype, float* e_w, int* slow_list, int* n_slow, cudaStream_t st);
 void td_launch_protein_embed(const float* feat, int n_protein, int fdim, const float* w, const float* b, const int* prot_node,

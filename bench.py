@@ -296,12 +296,26 @@ def main():
                                              'achieved': bytes_x / t_x / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': bytes_x / t_x / 1e9 / peak,
                                              'avg_launch_ms': t_x * 1e3, 'share_of_step': ms_x / tot if tot else None}
         if n_mlp:
-            # executed flops of the FFMA edge-MLP path: per x2h edge 2 MLPs x (128*128 + 20*128) MAC; per ligand-dst edge (h2x)
-            # (128*128 + 20*128) + (128*16 + 20*128) MAC
-            flops = 2.0 * (E * 2 * (128 * 128 + 20 * 128) + Nl * a.knn * ((128 * 128 + 20 * 128) + (128 * 16 + 20 * 128)))
-            t_m = ms_mlp / (n_mlp / 2) * 1e-3                       # per layer (x2h pair + h2x pair)
-            extra['edge_mlp'] = {'kernel': 'edge MLPs (mode %d, see tdiff_edge_mlp_mode)' % mode, 'executed_tflops': flops / t_m / 1e12,
-                                 'ms_per_layer': t_m * 1e3, 'share_of_step': ms_mlp / tot if tot else None}
+            # tensor-core work actually executed by the edge MLPs of one layer (x2h: hk + hv on all E rows; h2x: xk + xv on ligand
+            # destinations): per row 3 bf16 products x (128 x NOUT second Linear + 32 x 128 gaussian block) MAC on tcgen05
+            El = Nl * a.knn
+            mac_row = lambda nout: 3 * (128 * nout + 32 * 128)
+            flops = 2.0 * (E * 2 * mac_row(128) + El * (mac_row(128) + mac_row(16)))
+            t_m = ms_mlp / (n_mlp / 2) * 1e-3                       # per layer (x2h pair + h2x pair, incl. the slow-row pre-passes)
+            tpeak = None
+            try:
+                tpeak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['bf16_tflops_sustained'])
+                tsrc = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)'
+            except Exception:
+                tpeak, tsrc = 1400.0, 'fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)'
+            ach = flops / t_m / 1e12
+            extra['edge_mlp'] = {'kernel': 'edge_mlp_v3_kernel x4 per layer (engine mode %d)' % mode, 'bound': 'tensor', 'achieved': ach, 'peak': tpeak,
+                                 'unit': 'TFLOP/s', 'frac': ach / tpeak, 'traffic': None, 'peak_source': tsrc, 'executed_flops_per_layer': flops,
+                                 'ms_per_layer': t_m * 1e3, 'share_of_step': ms_mlp / tot if tot else None,
+                                 'note': 'bf16-split products count as executed flops (3 MMAs per fp32-class product); the kernel is bound by its '
+                                         'CUDA-core LayerNorm/split stage, see DESIGN.md section 6'}
+            if roofline is None:            # aggregation fused into the value-MLP epilogue: the dominant kernel is the edge MLP itself
+                roofline = dict(extra['edge_mlp'])
         extra['profile_ms_per_step_eager'] = tot / a.profile_steps if tot else None
         # canonical (unfused) attention aggregation on the same problem size through the stand-alone C-ABI operator: keys AND values
         # in HBM, algorithmic bytes E*1028 + N*1536; timed with CUDA events on the launch stream

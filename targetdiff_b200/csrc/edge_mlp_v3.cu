@@ -163,7 +163,49 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 // LayerNorm affine parameters travel as a kernel argument (constant bank: no L2 round trips in the row threads)
 struct LnParams { float g[128]; float b[128]; float b2[128]; };
+// Fused attention aggregation in the value-MLP epilogue (k == 32: the 32 rows of an epilogue warp are exactly the edges of one
+// destination): h[dst] += sum_e softmax_e(logits[e,head]) * e_w[e] * v[e]   (reference models/uni_transformer.py:73-83).
+struct AggArgs {
+  const float* logits;   // [E,16] written by the key-MLP launch; NULL = plain value output
+  const float* e_w;      // [E]
+  float* h;              // [N,128] node features, updated in place (row of a destination is touched by one warp only)
+  int n_nodes;
+};
 
+// Reduce 16 per-lane values over the 32 lanes of a warp with a transposing butterfly: 15 + 1 shuffles instead of 16 x 5.
+// On return lanes l and l^16 both hold the total (sum or max) of element (l & 15).
+template <bool MAX>
+__device__ __forceinline__ float warp_transpose_reduce16(float (&t)[16], int lane) {
+  auto op = [](float a, float b) { return MAX ? fmaxf(a, b) : a + b; };
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? t[i] : t[i + 8];
+    const float keep = up ? t[i + 8] : t[i];
+    t[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? t[i] : t[i + 4];
+    const float keep = up ? t[i + 4] : t[i];
+    t[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 2;
+    const float send = up ? t[i] : t[i + 2];
+    const float keep = up ? t[i + 2] : t[i];
+    t[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? t[0] : t[1];
+    const float keep = up ? t[1] : t[0];
+    t[0] = op(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+  }
+  return op(t[0], __shfl_xor_sync(0xffffffffu, t[0], 16));
+}
 // 8 consecutive values -> two bf16 pieces (16 bytes each); residual of the first piece is exact in fp32
 __device__ __forceinline__ void split8_store(uint32_t addr_p0, uint32_t addr_p1, const float (&y)[8]) {
   uint32_t h[4], l[4];
@@ -187,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, const unsigned char* __restrict__ etype,
                    const float* __restrict__ dist_arr, const int* __restrict__ row_nodes, long long n_rows, int k, TdMlp m,
                    const unsigned char* __restrict__ w2_image, const unsigned char* __restrict__ tab3_image, const float* __restrict__ offsets,
-                   float coeff, const float* __restrict__ tslow, const float* __restrict__ qnode, float* __restrict__ out, int dbg, const __grid_constant__ LnParams lp, long long* __restrict__ ts) {
+                   float coeff, const float* __restrict__ tslow, const float* __restrict__ qnode, float* __restrict__ out, AggArgs agg, int dbg, const __grid_constant__ LnParams lp, long long* __restrict__ ts) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sW = sbase + oW, sA = sbase + oA, sS = sbase + oS, sG = sbase + oG, sT = sbase + oT, sX = sbase + oX, sBar = sbase + oBar;
@@ -501,6 +543,55 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
                  __uint_as_float(v[11]) + lp.b2[11], __uint_as_float(v[12]) + lp.b2[12], __uint_as_float(v[13]) + lp.b2[13],
                  __uint_as_float(v[14]) + lp.b2[14], __uint_as_float(v[15]) + lp.b2[15]);
         }
+      } else if (qnode == nullptr && agg.logits != nullptr) {
+        // ---- value MLP with the attention aggregation fused in: this warp's 32 rows are the edges of destination 4*tile + warp
+        const long long dnode = tile * 4 + warp;
+        const bool active = dnode < agg.n_nodes;                       // warp-uniform
+        const long long e = dnode * 32 + lane;
+        const bool valid = active && src[e] >= 0;
+        float w[16];
+        {
+          float ew = 0.f;
+          if (valid) {
+            ew = agg.e_w[e];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(agg.logits + (size_t)e * TD_HEADS + 4 * i));
+              w[4 * i] = t4.x; w[4 * i + 1] = t4.y; w[4 * i + 2] = t4.z; w[4 * i + 3] = t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = -INFINITY;
+          }
+          // softmax over the 32 edges for the 16 heads: head hh's max / sum end up in lanes hh and hh+16, then are broadcast
+          float tmp[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) tmp[i] = w[i];
+          const float mx_mine = warp_transpose_reduce16<true>(tmp, lane);
+#pragma unroll
+          for (int hh = 0; hh < 16; ++hh) {
+            const float mx = __shfl_sync(0xffffffffu, mx_mine, hh);
+            w[hh] = valid ? expf(w[hh] - mx) : 0.0f;
+            tmp[hh] = w[hh];
+          }
+          const float l_mine = warp_transpose_reduce16<false>(tmp, lane);
+          const float inv_mine = l_mine > 0.0f ? 1.0f / l_mine : 0.0f;
+#pragma unroll
+          for (int hh = 0; hh < 16; ++hh) w[hh] = w[hh] * ew * __shfl_sync(0xffffffffu, inv_mine, hh);      // alpha * e_w
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + ph * 128u + (uint32_t)c0, v);
+          float t[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t[i] = w[c0 / 8 + i / 8] * (__uint_as_float(v[i]) + lp.b2[c0 + i]);
+          const float tot = warp_transpose_reduce16<false>(t, lane);
+          if (active && lane < 16 && !(dbg & 1)) {
+            float* hp = agg.h + (size_t)dnode * TD_H + c0 + lane;
+            *hp = *hp + tot;
+          }
+        }
       } else if (qnode == nullptr) {
         // ---- value MLPs: out[row, 0:128] = D + b2
         float* orow = out + (size_t)idx * 128;
@@ -626,7 +717,8 @@ edge_slow_kernel(const int* __restrict__ src, const unsigned char* __restrict__ 
 void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_rows,
                            int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
                            const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const int* slow_list, const int* n_slow,
-                           const float* qnode, float* out, int sm_count, cudaStream_t st) {
+                           const float* qnode, float* out, const float* agg_logits, const float* agg_e_w, float* agg_h, int agg_n_nodes,
+                           int sm_count, cudaStream_t st) {
   if (n_rows == 0) return;
   LnParams lp;
   memcpy(lp.g, h_ln_g, sizeof(lp.g));
@@ -648,6 +740,7 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
     edge_slow_kernel<<<(int)blocks, 256, 0, st>>>(src, etype, dist, row_nodes, n_rows, k, listed ? slow_list : nullptr, n_slow, m.tab, offsets,
                                                   coeff, tslow);
   }
+  AggArgs agg = {agg_logits, agg_e_w, agg_h, agg_n_nodes};
   static int dbg = -1;
   static long long* d_ts = nullptr;
   if (dbg < 0) {
@@ -657,10 +750,10 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
   }
   if (m.nout == 16)
     edge_mlp_v3_kernel<16><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_rows, k, m, w2_image, tab3_image, offsets, coeff, tslow,
-                                                         nullptr, out, dbg, lp, d_ts);
+                                                         nullptr, out, agg, dbg, lp, d_ts);
   else
     edge_mlp_v3_kernel<128><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_rows, k, m, w2_image, tab3_image, offsets, coeff, tslow,
-                                                          qnode, out, dbg, lp, d_ts);
+                                                          qnode, out, agg, dbg, lp, d_ts);
   if (d_ts && n_rows > 1000000) {          // dump the timeline of the first big launch, once
     static bool dumped = false;
     if (!dumped) {

@@ -543,10 +543,11 @@ struct Prof {
 bool fused_logits(const tdiff_engine* e) { return e->mlp_mode == 2 && e->mlp_v3; }
 void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
               long long n_rows, int K, const TdMlp& m, const float* offsets, float coeff, float* out, cudaStream_t st,
-              const float* qnode = nullptr) {
+              const float* qnode = nullptr, const float* agg_logits = nullptr, float* agg_h = nullptr, int agg_n = 0) {
   if (e->mlp_mode == 2 && e->mlp_v3 && m.w2_img && m.tab3_img)
     td_launch_edge_mlp_v3(P, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, m.tab3_img, offsets, coeff,
-                          e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena), e->host_arena.data() + (m.b2 - e->arena), e->tslow.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), qnode, out, e->sm_count, st);
+                          e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena), e->host_arena.data() + (m.b2 - e->arena), e->tslow.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), qnode, out, agg_logits, e->e_w.as<float>(), agg_h, agg_n,
+                          e->sm_count, st);
   else if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
     td_launch_edge_mlp_tc(P, xm, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, e->mlp_mode, offsets, coeff, out, e->sm_count, st);
   else
@@ -587,18 +588,21 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     // ---- x2h: h <- h + sum_e alpha * v * e_w
     node_side(e, h, N, ly.x2h, P, q, st);
     if (e->mlp_mode != 0) { td_launch_edge_geom(xm[cur], src, N, K, e->dist.as<float>(), st); e->launches += 1; }
+    // k == 32: a 128-row tile is 4 complete destinations -> the value launch also performs the softmax aggregation (h += ...)
+    const bool fuse_agg = fused_logits(e) && K == 32 && !getenv("TDIFF_NO_FUSED_AGG");
     {
       Prof pr(e, st, EV_EDGE_MLP);
       edge_mlp(e, P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st,
                fused_logits(e) ? q : nullptr);
-      edge_mlp(e, P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), st);
+      edge_mlp(e, P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), st, nullptr,
+               fuse_agg ? e->kbuf.as<float>() : nullptr, fuse_agg ? h : nullptr, N);
     }
-    {
+    if (!fuse_agg) {
       Prof pr(e, st, EV_AGG_H);
       if (fused_logits(e)) td_launch_aggregate_h_logits(e->kbuf.as<float>(), e->vbuf.as<float>(), e->e_w.as<float>(), src, h, h, N, K, st);
       else td_launch_aggregate_h(e->kbuf.as<float>(), e->vbuf.as<float>(), e->e_w.as<float>(), src, q, h, h, N, K, st);
     }
-    e->launches += 5;
+    e->launches += fuse_agg ? 6 : (fused_logits(e) ? 7 : 5);
     if (fix_x || Nl == 0) continue;     // h2x only moves ligand atoms; with fix_x its result is discarded (:204-206)
     // ---- h2x: x_lig <- x_lig + mean_heads sum_e alpha * v * e_w * (x_dst - x_src), destinations = ligand atoms only
     node_side(e, h, N, ly.h2x, P, q, st);

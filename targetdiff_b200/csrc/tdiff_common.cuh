@@ -129,7 +129,8 @@ void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, con
 void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_rows,
                            int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
                            const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const int* slow_list, const int* n_slow,
-                           const float* qnode, float* out, int sm_count, cudaStream_t st);
+                           const float* qnode, float* out, const float* agg_logits, const float* agg_e_w, float* agg_h, int agg_n_nodes,
+                           int sm_count, cudaStream_t st);
 void td_launch_rows_tc(int mode, const float* in, int ldi, int in_off, long long n_rows, TdMlp m, const unsigned char* w_image, int pieces, float* out,
                        int ldo, int nblocks, int sm_count, cudaStream_t st);
 void td_launch_aggregate_h(const float* kbuf, const float* vbuf, const float* e_w, const int* src, const float* q, const float* h_in,

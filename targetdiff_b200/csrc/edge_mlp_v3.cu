@@ -526,6 +526,29 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       const long long tile = blockIdx.x + it * gridDim.x;
       const uint32_t ph = (uint32_t)(it & 1), ph2 = (uint32_t)((it >> 1) & 1);
       if (warp == 0) stamp(3, it, 0);
+      // fused aggregation (value launch, k == 32): everything that does not depend on the accumulator is fetched before waiting for it
+      const bool do_agg = NOUT == 128 && qnode == nullptr && agg.logits != nullptr;
+      const long long dnode = tile * 4 + warp;
+      const bool active = do_agg && dnode < agg.n_nodes;              // warp-uniform
+      bool valid_e = false;
+      float w[16], hin[8], ew = 0.f;
+      if (do_agg) {
+        const long long e = dnode * 32 + lane;
+        valid_e = active && src[e] >= 0;
+        if (valid_e) {
+          ew = agg.e_w[e];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(agg.logits + (size_t)e * TD_HEADS + 4 * i));
+            w[4 * i] = t4.x; w[4 * i + 1] = t4.y; w[4 * i + 2] = t4.z; w[4 * i + 3] = t4.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = -INFINITY;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hin[j] = (active && lane < 16) ? agg.h[(size_t)dnode * TD_H + 16 * j + lane] : 0.0f;
+      }
       mbar_wait_relaxed(bar(B_D_FULL0 + (int)ph), ph2);
       if (warp == 0) stamp(3, it, 1);
       tc_fence_after();
@@ -543,26 +566,9 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
                  __uint_as_float(v[11]) + lp.b2[11], __uint_as_float(v[12]) + lp.b2[12], __uint_as_float(v[13]) + lp.b2[13],
                  __uint_as_float(v[14]) + lp.b2[14], __uint_as_float(v[15]) + lp.b2[15]);
         }
-      } else if (qnode == nullptr && agg.logits != nullptr) {
+      } else if (do_agg) {
         // ---- value MLP with the attention aggregation fused in: this warp's 32 rows are the edges of destination 4*tile + warp
-        const long long dnode = tile * 4 + warp;
-        const bool active = dnode < agg.n_nodes;                       // warp-uniform
-        const long long e = dnode * 32 + lane;
-        const bool valid = active && src[e] >= 0;
-        float w[16];
         {
-          float ew = 0.f;
-          if (valid) {
-            ew = agg.e_w[e];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(agg.logits + (size_t)e * TD_HEADS + 4 * i));
-              w[4 * i] = t4.x; w[4 * i + 1] = t4.y; w[4 * i + 2] = t4.z; w[4 * i + 3] = t4.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] = -INFINITY;
-          }
           // softmax over the 32 edges for the 16 heads: head hh's max / sum end up in lanes hh and hh+16, then are broadcast
           float tmp[16];
 #pragma unroll
@@ -571,7 +577,7 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
 #pragma unroll
           for (int hh = 0; hh < 16; ++hh) {
             const float mx = __shfl_sync(0xffffffffu, mx_mine, hh);
-            w[hh] = valid ? expf(w[hh] - mx) : 0.0f;
+            w[hh] = valid_e ? expf(w[hh] - mx) : 0.0f;
             tmp[hh] = w[hh];
           }
           const float l_mine = warp_transpose_reduce16<false>(tmp, lane);
@@ -579,18 +585,16 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
 #pragma unroll
           for (int hh = 0; hh < 16; ++hh) w[hh] = w[hh] * ew * __shfl_sync(0xffffffffu, inv_mine, hh);      // alpha * e_w
         }
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c0 = 16 * j;
           uint32_t v[16];
           tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + ph * 128u + (uint32_t)c0, v);
           float t[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) t[i] = w[c0 / 8 + i / 8] * (__uint_as_float(v[i]) + lp.b2[c0 + i]);
           const float tot = warp_transpose_reduce16<false>(t, lane);
-          if (active && lane < 16 && !(dbg & 1)) {
-            float* hp = agg.h + (size_t)dnode * TD_H + c0 + lane;
-            *hp = *hp + tot;
-          }
+          if (active && lane < 16 && !(dbg & 1)) agg.h[(size_t)dnode * TD_H + c0 + lane] = hin[j] + tot;
         }
       } else if (qnode == nullptr) {
         // ---- value MLPs: out[row, 0:128] = D + b2
@@ -746,18 +750,18 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
   if (dbg < 0) {
     const char* e = getenv("TDIFF_V3_DBG");
     dbg = e ? atoi(e) : 0;
-    if (getenv("TDIFF_V3_TS")) { cudaMalloc(&d_ts, 16 * 4 * 8 * 8); cudaMemset(d_ts, 0, 16 * 4 * 8 * 8); }
+    if (getenv("TDIFF_V3_TS")) cudaMalloc(&d_ts, 16 * 4 * 8 * 8);
   }
+  if (d_ts) cudaMemsetAsync(d_ts, 0, 16 * 4 * 8 * 8, st);
   if (m.nout == 16)
     edge_mlp_v3_kernel<16><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_rows, k, m, w2_image, tab3_image, offsets, coeff, tslow,
                                                          nullptr, out, agg, dbg, lp, d_ts);
   else
     edge_mlp_v3_kernel<128><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_rows, k, m, w2_image, tab3_image, offsets, coeff, tslow,
                                                           qnode, out, agg, dbg, lp, d_ts);
-  if (d_ts && n_rows > 1000000) {          // dump the timeline of the first big launch, once
-    static bool dumped = false;
-    if (!dumped) {
-      dumped = true;
+  if (d_ts && n_rows > 1000000) {          // dump the timeline of the TDIFF_V3_TS-th big launch, once
+    static int seen = 0;
+    if (++seen == atoi(getenv("TDIFF_V3_TS"))) {
       long long h[16 * 4 * 8];
       cudaStreamSynchronize(st);
       cudaMemcpy(h, d_ts, sizeof(h), cudaMemcpyDeviceToHost);

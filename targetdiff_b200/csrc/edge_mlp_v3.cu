@@ -699,21 +699,41 @@ edge_slow_kernel(const int* __restrict__ src, const unsigned char* __restrict__ 
       dist = dist_arr[e];
       if (src[e] < 0 || ty == 3) row = -1;
     }
-    for (unsigned mask = __ballot_sync(0xffffffffu, row >= 0); mask; mask &= mask - 1) {
-      const int rr = __ffs(mask) - 1;
-      const long long rrow = __shfl_sync(0xffffffffu, row, rr);
-      const int tr = __shfl_sync(0xffffffffu, ty, rr);
-      const float tmu = __shfl_sync(0xffffffffu, dist, rr) - mu;
-      const float gj = expf(coeff * (tmu * tmu));
-      const float* tb = tab + (size_t)tr * TD_TAB * TD_H + 4 * lane;
-      float4 v = __ldg(reinterpret_cast<const float4*>(tb + TD_NG * TD_H));
-#pragma unroll 5
-      for (int jj = 0; jj < TD_NG; ++jj) {
-        const float g = __shfl_sync(0xffffffffu, gj, jj);
-        const float4 cj = __ldg(reinterpret_cast<const float4*>(tb + jj * TD_H));
-        v.x = fmaf(g, cj.x, v.x); v.y = fmaf(g, cj.y, v.y); v.z = fmaf(g, cj.z, v.z); v.w = fmaf(g, cj.w, v.w);
+    // The kernel is bound by L1 bandwidth (21 table rows x 512 B per edge row), so edge rows of the same type are processed four at
+    // a time in registers: one table-row load feeds four accumulators.
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+      unsigned mask = __ballot_sync(0xffffffffu, row >= 0 && ty == t);
+      const float* tb = tab + (size_t)t * TD_TAB * TD_H + 4 * lane;
+      while (mask) {
+        int rr[4];
+        long long rrow[4];
+        float gj[4];
+        float4 v[4];
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(tb + TD_NG * TD_H));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          rr[u] = mask ? __ffs(mask) - 1 : -1;
+          if (mask) mask &= mask - 1;
+          const int srcl = rr[u] >= 0 ? rr[u] : 0;
+          rrow[u] = __shfl_sync(0xffffffffu, row, srcl);
+          const float tmu = __shfl_sync(0xffffffffu, dist, srcl) - mu;
+          gj[u] = expf(coeff * (tmu * tmu));
+          v[u] = c0;
+        }
+#pragma unroll 4
+        for (int jj = 0; jj < TD_NG; ++jj) {
+          const float4 cj = __ldg(reinterpret_cast<const float4*>(tb + jj * TD_H));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float g = __shfl_sync(0xffffffffu, gj[u], jj);
+            v[u].x = fmaf(g, cj.x, v[u].x); v[u].y = fmaf(g, cj.y, v[u].y); v[u].z = fmaf(g, cj.z, v[u].z); v[u].w = fmaf(g, cj.w, v[u].w);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (rr[u] >= 0) *reinterpret_cast<float4*>(tslow + (size_t)rrow[u] * TD_H + 4 * lane) = v[u];
       }
-      *reinterpret_cast<float4*>(tslow + (size_t)rrow * TD_H + 4 * lane) = v;
     }
   }
 }

@@ -444,12 +444,12 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(db * 128 + c0), v);
         if (idx < n_rows) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            const float4 bia = lds128(smem_u32(s_b2 + c0 + c));
-            float4 o;
-            o.x = __uint_as_float(v[c]) + bia.x; o.y = __uint_as_float(v[c + 1]) + bia.y;
-            o.z = __uint_as_float(v[c + 2]) + bia.z; o.w = __uint_as_float(v[c + 3]) + bia.w;
-            *reinterpret_cast<float4*>(orow + c0 + c) = o;
+          for (int c = 0; c < 32; c += 8) {          // 32-byte stores: one full sector per thread
+            const float4 ba = lds128(smem_u32(s_b2 + c0 + c)), bb = lds128(smem_u32(s_b2 + c0 + c + 4));
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(orow + c0 + c), "f"(__uint_as_float(v[c]) + ba.x),
+                         "f"(__uint_as_float(v[c + 1]) + ba.y), "f"(__uint_as_float(v[c + 2]) + ba.z), "f"(__uint_as_float(v[c + 3]) + ba.w),
+                         "f"(__uint_as_float(v[c + 4]) + bb.x), "f"(__uint_as_float(v[c + 5]) + bb.y), "f"(__uint_as_float(v[c + 6]) + bb.z),
+                         "f"(__uint_as_float(v[c + 7]) + bb.w) : "memory");
           }
         }
       }

@@ -15,7 +15,8 @@ __global__ void __launch_bounds__(EC_WARPS * 32)
 edge_const_kernel(const float4* __restrict__ xm, const int* __restrict__ src, int* __restrict__ src_prev, int have_prev, int n_nodes, int k,
                   const float* __restrict__ offsets, float coeff, const float* __restrict__ w1t, const float* __restrict__ b1,
                   const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ w2, float b2,
-                  unsigned char* __restrict__ etype, float* __restrict__ e_w, int* __restrict__ slow_list, int* __restrict__ n_slow) {
+                  unsigned char* __restrict__ etype, float* __restrict__ e_w, int* __restrict__ slow_list, int* __restrict__ n_slow,
+                  unsigned char* __restrict__ rel_flag) {
   __shared__ float s_w1t[TD_NG * TD_H];
   __shared__ float s_b1[TD_H], s_g[TD_H], s_b[TD_H], s_w2[TD_H];
   for (int i = threadIdx.x; i < TD_NG * TD_H; i += blockDim.x) s_w1t[i] = w1t[i];
@@ -38,6 +39,14 @@ edge_const_kernel(const float4* __restrict__ xm, const int* __restrict__ src, in
         src_prev[e0 + j] = s;
       }
       if (s >= 0) touch = touch || (xm[s].w != 0.0f);
+    }
+    // "relevant" nodes = ligand atoms and their neighbours: the only rows the h2x sub-layers (and the last x2h) need
+    if (rel_flag && xd.w != 0.0f) {
+      if (lane == 0) rel_flag[node] = 1;
+      for (int j = lane; j < k; j += 32) {
+        const int s = src[e0 + j];
+        if (s >= 0) rel_flag[s] = 1;
+      }
     }
     same = __all_sync(0xffffffffu, same);
     touch = __any_sync(0xffffffffu, touch);
@@ -80,13 +89,14 @@ edge_const_kernel(const float4* __restrict__ xm, const int* __restrict__ src, in
 
 void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int have_prev, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
-                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, cudaStream_t st) {
+                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, unsigned char* rel_flag, cudaStream_t st) {
   if (n_nodes == 0) return;
   int blocks = (n_nodes + EC_WARPS - 1) / EC_WARPS;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (n_slow) cudaMemsetAsync(n_slow, 0, sizeof(int), st);
+  if (rel_flag) cudaMemsetAsync(rel_flag, 0, (size_t)n_nodes, st);
   edge_const_kernel<<<blocks, EC_WARPS * 32, 0, st>>>(xm, src, src_prev, have_prev, n_nodes, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2, etype,
-                                                      e_w, slow_list, n_slow);
+                                                      e_w, slow_list, n_slow, rel_flag);
 }
 
 // Per-layer edge length |x_dst - x_src| (reference models/uni_transformer.py:188-189) for every slot, from the layer's input
@@ -107,4 +117,16 @@ __global__ void edge_geom_kernel(const float4* __restrict__ xm, const int* __res
 void td_launch_edge_geom(const float4* xm, const int* src, int n_nodes, int k, float* dist, cudaStream_t st) {
   const long long n = (long long)n_nodes * k;
   if (n > 0) edge_geom_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(xm, src, n, k, dist);
+}
+
+// Compact the relevant-node flags into a list (order irrelevant: every row is processed independently).  The list is padded to a
+// multiple of 4 entries with -1 so that a 128-row edge tile (k == 32) always holds 4 list entries.
+__global__ void rel_compact_kernel(const unsigned char* __restrict__ flag, int n_nodes, int* __restrict__ rel_list, int* __restrict__ n_rel) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_nodes && flag[i]) rel_list[atomicAdd(n_rel, 1)] = i;
+}
+void td_launch_rel_compact(const unsigned char* flag, int n_nodes, int* rel_list, int* n_rel, cudaStream_t st) {
+  if (n_nodes == 0) return;
+  cudaMemsetAsync(n_rel, 0, sizeof(int), st);
+  rel_compact_kernel<<<(n_nodes + 255) / 256, 256, 0, st>>>(flag, n_nodes, rel_list, n_rel);
 }

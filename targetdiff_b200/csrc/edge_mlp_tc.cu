@@ -164,8 +164,10 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
 // MODE 1: dense rows: out[:, y*128:(y+1)*128] = in[:, :128] . W_y^T + b_y for column block y = blockIdx.y (node projection)
 // MODE 2: LN rows:    out = relu(LN(in[:, in_off:in_off+128])) . W^T + b                                   (query MLP tail)
 struct TcRows {
-  const float* in;   // [n_rows, ldi]
+  const float* in;       // [*, ldi]
   int ldi, in_off, ldo;
+  const int* row_list;   // optional: logical row i reads in[row_list[i]] and writes out[row_list[i]] (a node subset)
+  const int* d_n_rows;   // optional: number of logical rows lives in device memory (list compacted on the device)
 };
 
 template <int NP, int NBUF, int NSETS, int MODE>
@@ -215,6 +217,7 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
+  if (MODE != 0 && rw.d_n_rows) n_rows = *rw.d_n_rows;
   const long long n_tiles = (n_rows + 127) / 128;
   const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -239,7 +242,10 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row0 + r < n_rows) v = ldg_stream(rw.in + (size_t)(row0 + r) * rw.ldi + rw.in_off + 4 * lane);
+          if (row0 + r < n_rows) {
+            const long long src_row = rw.row_list ? rw.row_list[row0 + r] : row0 + r;
+            v = ldg_stream(rw.in + (size_t)src_row * rw.ldi + rw.in_off + 4 * lane);
+          }
           acc[r][0] = v.x; acc[r][1] = v.y; acc[r][2] = v.z; acc[r][3] = v.w;
         }
         if (MODE == 2) {
@@ -437,7 +443,8 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
       mbar_wait_relaxed(bar_d_full + 8 * db, phd);
       tc_fence_after();
       const long long idx = tile * 128 + warp * 32 + lane;
-      float* orow = out + (size_t)idx * (MODE == 0 ? 128 : rw.ldo) + (MODE == 1 ? blockIdx.y * 128 : 0);
+      const long long orow_i = (MODE != 0 && rw.row_list && idx < n_rows) ? rw.row_list[idx] : idx;
+      float* orow = out + (size_t)orow_i * (MODE == 0 ? 128 : rw.ldo) + (MODE == 1 ? blockIdx.y * 128 : 0);
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t v[32];
@@ -490,7 +497,7 @@ void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, con
                            const int* row_nodes, long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
                            float* out, int sm_count, cudaStream_t st) {
   if (n_rows == 0) return;
-  TcRows rw = {nullptr, 0, 0, 128};
+  TcRows rw = {nullptr, 0, 0, 128, nullptr, nullptr};
   if (pieces == 2) launch_tc<2, 2, 2, 0>(P, xm, src, etype, dist, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, rw, 1, sm_count, st);
   else launch_tc<3, 1, 1, 0>(P, xm, src, etype, dist, row_nodes, n_rows, k, m, w2_image, offsets, coeff, out, rw, 1, sm_count, st);
 }
@@ -499,9 +506,9 @@ void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, con
 //   mode 1: out[n_rows, nblocks*128] = in[n_rows,128] . W^T + bias, W given as `nblocks` images of [128 x 128] (node projection, nblocks = 5)
 //   mode 2: out[n_rows,128] = relu(LN(in[:, in_off:in_off+128]; m.ln_g, m.ln_b)) . W^T + m.b2                         (query MLP tail)
 void td_launch_rows_tc(int mode, const float* in, int ldi, int in_off, long long n_rows, TdMlp m, const unsigned char* w_image, int pieces, float* out,
-                       int ldo, int nblocks, int sm_count, cudaStream_t st) {
-  if (n_rows == 0) return;
-  TcRows rw = {in, ldi, in_off, ldo};
+                       int ldo, int nblocks, const int* row_list, const int* d_n_rows, int sm_count, cudaStream_t st) {
+  if (n_rows == 0) return;          // with d_n_rows, n_rows is only the upper bound used to size the grid
+  TcRows rw = {in, ldi, in_off, ldo, row_list, d_n_rows};
   if (mode == 1) {
     if (pieces == 2) launch_tc<2, 2, 2, 1>(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_rows, 1, m, w_image, nullptr, 0.f, out, rw, nblocks, sm_count, st);
     else launch_tc<3, 1, 1, 1>(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_rows, 1, m, w_image, nullptr, 0.f, out, rw, nblocks, sm_count, st);

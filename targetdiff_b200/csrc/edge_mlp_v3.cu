@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, const unsigned char* __restrict__ etype,
                    const float* __restrict__ dist_arr, const int* __restrict__ row_nodes, long long n_rows, int k, TdMlp m,
                    const unsigned char* __restrict__ w2_image, const unsigned char* __restrict__ tab3_image, const float* __restrict__ offsets,
-                   float coeff, const float* __restrict__ tslow, const float* __restrict__ qnode, float* __restrict__ out, AggArgs agg, int dbg, const __grid_constant__ LnParams lp, long long* __restrict__ ts) {
+                   float coeff, const float* __restrict__ tslow, const float* __restrict__ qnode, float* __restrict__ out, AggArgs agg, const int* __restrict__ d_n_dst, int dbg, const __grid_constant__ LnParams lp, long long* __restrict__ ts) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sW = sbase + oW, sA = sbase + oA, sS = sbase + oS, sG = sbase + oG, sT = sbase + oT, sX = sbase + oX, sBar = sbase + oBar;
@@ -274,6 +274,7 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  if (d_n_dst) n_rows = (long long)(*d_n_dst) * k;        // destination subset compacted on the device (row_nodes list)
   const long long n_tiles = (n_rows + 127) / 128;
   const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -528,18 +529,19 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       if (warp == 0) stamp(3, it, 0);
       // fused aggregation (value launch, k == 32): everything that does not depend on the accumulator is fetched before waiting for it
       const bool do_agg = NOUT == 128 && qnode == nullptr && agg.logits != nullptr;
-      const long long dnode = tile * 4 + warp;
-      const bool active = do_agg && dnode < agg.n_nodes;              // warp-uniform
+      const long long dslot = tile * 4 + warp;                        // k == 32: destination index of this warp's 32 rows
+      const bool active = do_agg && dslot * 32 < n_rows;              // warp-uniform
+      const long long dnode = (active && row_nodes) ? row_nodes[dslot] : dslot;
       bool valid_e = false;
       float w[16], hin[8], ew = 0.f;
       if (do_agg) {
-        const long long e = dnode * 32 + lane;
+        const long long e = dnode * 32 + lane;                         // slot (src, e_w); logits are indexed by the launch's row
         valid_e = active && src[e] >= 0;
         if (valid_e) {
           ew = agg.e_w[e];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(agg.logits + (size_t)e * TD_HEADS + 4 * i));
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(agg.logits + (size_t)(dslot * 32 + lane) * TD_HEADS + 4 * i));
             w[4 * i] = t4.x; w[4 * i + 1] = t4.y; w[4 * i + 2] = t4.z; w[4 * i + 3] = t4.w;
           }
         } else {
@@ -674,10 +676,11 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
 __global__ void __launch_bounds__(256)
 edge_slow_kernel(const int* __restrict__ src, const unsigned char* __restrict__ etype, const float* __restrict__ dist_arr,
                  const int* __restrict__ row_nodes, long long n_rows, int k, const int* __restrict__ slow_list, const int* __restrict__ n_slow,
-                 const float* __restrict__ tab, const float* __restrict__ offsets, float coeff, float* __restrict__ tslow) {
+                 const int* __restrict__ d_n_dst, const float* __restrict__ tab, const float* __restrict__ offsets, float coeff, float* __restrict__ tslow) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * 8;
   const float mu = offsets[lane < TD_NG ? lane : 0];
+  if (d_n_dst) n_rows = (long long)(*d_n_dst) * k;
   const long long n_items = slow_list ? (long long)*n_slow : n_rows;
   // 32 items per warp iteration: every lane fetches the metadata of one row (one latency for 32 rows), rows are then processed in turn
   for (long long i0 = warp0 * 32; i0 < n_items; i0 += nwarps * 32) {
@@ -742,7 +745,7 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
                            int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
                            const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const int* slow_list, const int* n_slow,
                            const float* qnode, float* out, const float* agg_logits, const float* agg_e_w, float* agg_h, int agg_n_nodes,
-                           int sm_count, cudaStream_t st) {
+                           const int* d_n_dst, int sm_count, cudaStream_t st) {
   if (n_rows == 0) return;
   LnParams lp;
   memcpy(lp.g, h_ln_g, sizeof(lp.g));
@@ -759,9 +762,9 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
   {
     const bool listed = (row_nodes == nullptr) && slow_list;            // x2h: iterate the compacted list; h2x: scan the (few) rows
-    long long blocks = listed ? sm_count * 8 : (n_rows + 7) / 8;
+    long long blocks = (listed || d_n_dst) ? sm_count * 8 : (n_rows + 255) / 256;      // a block covers 256 rows per grid-stride iteration
     if (blocks > sm_count * 8) blocks = sm_count * 8;
-    edge_slow_kernel<<<(int)blocks, 256, 0, st>>>(src, etype, dist, row_nodes, n_rows, k, listed ? slow_list : nullptr, n_slow, m.tab, offsets,
+    edge_slow_kernel<<<(int)blocks, 256, 0, st>>>(src, etype, dist, row_nodes, n_rows, k, listed ? slow_list : nullptr, n_slow, d_n_dst, m.tab, offsets,
                                                   coeff, tslow);
   }
   AggArgs agg = {agg_logits, agg_e_w, agg_h, agg_n_nodes};
@@ -775,10 +778,10 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
   if (d_ts) cudaMemsetAsync(d_ts, 0, 16 * 4 * 8 * 8, st);
   if (m.nout == 16)
     edge_mlp_v3_kernel<16><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_rows, k, m, w2_image, tab3_image, offsets, coeff, tslow,
-                                                         nullptr, out, agg, dbg, lp, d_ts);
+                                                         nullptr, out, agg, d_n_dst, dbg, lp, d_ts);
   else
     edge_mlp_v3_kernel<128><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_rows, k, m, w2_image, tab3_image, offsets, coeff, tslow,
-                                                          qnode, out, agg, dbg, lp, d_ts);
+                                                          qnode, out, agg, d_n_dst, dbg, lp, d_ts);
   if (d_ts && n_rows > 1000000) {          // dump the timeline of the TDIFF_V3_TS-th big launch, once
     static int seen = 0;
     if (++seen == atoi(getenv("TDIFF_V3_TS"))) {

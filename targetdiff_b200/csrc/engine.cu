@@ -73,9 +73,11 @@ struct tdiff_engine {
   const float *t_c0 = nullptr, *t_ct = nullptr, *t_logvar = nullptr, *t_la = nullptr, *t_l1ma = nullptr, *t_lca = nullptr, *t_l1mca = nullptr;
   // ---- batch
   bool bound = false, has_ligand = false, have_graph = false;
+  bool restrict_last = false;           // sampling loop only: the last layer's x2h is evaluated for the relevant nodes only
   bool have_prev = false;               // src_prev / etype / e_w hold the previous forward's graph of this batch (edge_const reuse)
   int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
   DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
+  DevBuf rel_flag, rel_list, n_rel;
   DevBuf xm0, xm1, offset, h0, h, P, q, src, src_prev, etype, e_w, dist, tslow, slow_list, n_slow, kbuf, vbuf, v16, lig_pos, lig_v, logits;
   DevBuf step, err_flag, node_off, total_edges;
   DevBuf stage[8];   // staging for tdiff_sample_host
@@ -409,7 +411,7 @@ extern "C" void tdiff_destroy(tdiff_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   DevBuf* bufs[] = {&e->node_ptr, &e->prot_ptr, &e->prot_node, &e->prot_graph, &e->lig_node, &e->lig_graph, &e->node_lig, &e->xm0, &e->xm1,
-                    &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->src_prev, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->slow_list, &e->n_slow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
+                    &e->rel_flag, &e->rel_list, &e->n_rel, &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->src_prev, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->slow_list, &e->n_slow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
                     &e->lig_v, &e->logits, &e->step, &e->err_flag, &e->node_off, &e->total_edges};
   for (auto* b : bufs) b->release();
   for (auto& b : e->stage) b.release();
@@ -458,7 +460,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   if (e->mlp_mode == 2 && e->mlp_v3) bad |= e->tslow.ensure(slots * TD_H * 4) | e->slow_list.ensure(slots * 4) | e->n_slow.ensure(16);   // row-indexed, only ligand-touching rows are touched
   bad |= e->kbuf.ensure(slots * TD_H * 4) | e->vbuf.ensure(slots * TD_H * 4) | e->v16.ensure((size_t)Nl * K * TD_HEADS * 4 + 16);
   bad |= e->lig_pos.ensure(Nl * 16 + 16) | e->lig_v.ensure(Nl * 4 + 4) | e->logits.ensure((size_t)Nl * e->cfg.num_classes * 4 + 4);
-  bad |= e->node_off.ensure(N * 8);
+  bad |= e->node_off.ensure(N * 8) | e->rel_flag.ensure(N + 16) | e->rel_list.ensure(N * 4 + 64) | e->n_rel.ensure(16);
   if (bad) return set_err(TDIFF_ECUDA, "out of device memory binding a batch of %lld nodes (%zu edge slots)", N, slots);
   CK(cudaMemcpyAsync(e->node_ptr.p, node_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->prot_ptr.p, prot_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -543,11 +545,12 @@ struct Prof {
 bool fused_logits(const tdiff_engine* e) { return e->mlp_mode == 2 && e->mlp_v3; }
 void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
               long long n_rows, int K, const TdMlp& m, const float* offsets, float coeff, float* out, cudaStream_t st,
-              const float* qnode = nullptr, const float* agg_logits = nullptr, float* agg_h = nullptr, int agg_n = 0) {
+              const float* qnode = nullptr, const float* agg_logits = nullptr, float* agg_h = nullptr, int agg_n = 0,
+              const int* d_n_dst = nullptr) {
   if (e->mlp_mode == 2 && e->mlp_v3 && m.w2_img && m.tab3_img)
     td_launch_edge_mlp_v3(P, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, m.tab3_img, offsets, coeff,
                           e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena), e->host_arena.data() + (m.b2 - e->arena), e->tslow.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), qnode, out, agg_logits, e->e_w.as<float>(), agg_h, agg_n,
-                          e->sm_count, st);
+                          d_n_dst, e->sm_count, st);
   else if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
     td_launch_edge_mlp_tc(P, xm, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, e->mlp_mode, offsets, coeff, out, e->sm_count, st);
   else
@@ -555,12 +558,14 @@ void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src,
 }
 
 // node-side GEMMs: P = h . Wn^T + bn ; q = relu(LN(P[:,512:640])) . W2q^T + b2q   (tensor cores unless TDIFF_EDGE_MLP=simt)
-void node_side(tdiff_engine* e, const float* h, int N, const TdSubLayer& sl, float* P, float* q, cudaStream_t st) {
+// `rows` / `d_n` (optional): restrict to a node subset given as a device list (+ device count); other rows of P / q are left stale
+void node_side(tdiff_engine* e, const float* h, int N, const TdSubLayer& sl, float* P, float* q, cudaStream_t st, const int* rows = nullptr,
+               const int* d_n = nullptr) {
   if (e->mlp_mode != 0 && sl.wn_img && sl.q.w2_img) {
     TdMlp pm = sl.q;
     pm.b2 = sl.bn;                 // mode 1 reads the per-column-block bias through m.b2
-    td_launch_rows_tc(1, h, TD_H, 0, N, pm, sl.wn_img, e->mlp_mode, P, TD_NPROJ, TD_NPROJ / TD_H, e->sm_count, st);
-    td_launch_rows_tc(2, P, TD_NPROJ, 512, N, sl.q, sl.q.w2_img, e->mlp_mode, q, TD_H, 1, e->sm_count, st);
+    td_launch_rows_tc(1, h, TD_H, 0, N, pm, sl.wn_img, e->mlp_mode, P, TD_NPROJ, TD_NPROJ / TD_H, rows, d_n, e->sm_count, st);
+    td_launch_rows_tc(2, P, TD_NPROJ, 512, N, sl.q, sl.q.w2_img, e->mlp_mode, q, TD_H, 1, rows, d_n, e->sm_count, st);
   } else {
     td_launch_node_proj(h, N, sl.wn_t, sl.bn, P, st);
     td_launch_node_q(P, N, sl.q, q, st);
@@ -580,7 +585,8 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
   td_launch_init_h(e->h0.as<float>(), xm[0], e->lig_v.as<int>(), e->node_lig.as<int>(), e->wl_t, e->bl, N, h, st);
   td_launch_knn(xm[0], e->node_ptr.as<int>(), e->B, e->max_ng, K, e->src.as<int>(), st);
   td_launch_edge_const(xm[0], src, e->src_prev.as<int>(), e->have_prev ? 1 : 0, N, K, e->ew_off, e->ew_coeff, e->ew_w1t, e->ew_b1, e->ew_g, e->ew_b, e->ew_w2, e->ew_b2,
-                       e->etype.as<unsigned char>(), e->e_w.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), st);
+                       e->etype.as<unsigned char>(), e->e_w.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), e->rel_flag.as<unsigned char>(), st);
+  td_launch_rel_compact(e->rel_flag.as<unsigned char>(), N, e->rel_list.as<int>(), e->n_rel.as<int>(), st);
   e->launches += 4;
   int cur = 0;
   for (size_t l = 0; l < e->layers.size(); ++l) {
@@ -590,12 +596,17 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     if (e->mlp_mode != 0) { td_launch_edge_geom(xm[cur], src, N, K, e->dist.as<float>(), st); e->launches += 1; }
     // k == 32: a 128-row tile is 4 complete destinations -> the value launch also performs the softmax aggregation (h += ...)
     const bool fuse_agg = fused_logits(e) && K == 32 && !getenv("TDIFF_NO_FUSED_AGG");
+    // sampling loop, last layer: only the ligand atoms' features feed the type head and only ligand atoms + their neighbours feed
+    // the last h2x, so x2h is evaluated for those destinations only (device-compacted list; final_h of other nodes is not produced)
+    const bool sub = fuse_agg && e->restrict_last && l + 1 == e->layers.size() && !getenv("TDIFF_NO_RESTRICT");
+    const int* rows = sub ? e->rel_list.as<int>() : nullptr;
+    const int* d_n = sub ? e->n_rel.as<int>() : nullptr;
     {
       Prof pr(e, st, EV_EDGE_MLP);
-      edge_mlp(e, P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st,
-               fused_logits(e) ? q : nullptr);
-      edge_mlp(e, P, xm[cur], src, etype, nullptr, (long long)N * K, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), st, nullptr,
-               fuse_agg ? e->kbuf.as<float>() : nullptr, fuse_agg ? h : nullptr, N);
+      edge_mlp(e, P, xm[cur], src, etype, rows, (long long)N * K, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st,
+               fused_logits(e) ? q : nullptr, nullptr, nullptr, 0, d_n);
+      edge_mlp(e, P, xm[cur], src, etype, rows, (long long)N * K, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), st, nullptr,
+               fuse_agg ? e->kbuf.as<float>() : nullptr, fuse_agg ? h : nullptr, N, d_n);
     }
     if (!fuse_agg) {
       Prof pr(e, st, EV_AGG_H);
@@ -605,7 +616,10 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     e->launches += fuse_agg ? 6 : (fused_logits(e) ? 7 : 5);
     if (fix_x || Nl == 0) continue;     // h2x only moves ligand atoms; with fix_x its result is discarded (:204-206)
     // ---- h2x: x_lig <- x_lig + mean_heads sum_e alpha * v * e_w * (x_dst - x_src), destinations = ligand atoms only
-    node_side(e, h, N, ly.h2x, P, q, st);
+    {
+      const bool rel = fused_logits(e) && !getenv("TDIFF_NO_RESTRICT");      // h2x only reads P / q of ligand atoms and their neighbours
+      node_side(e, h, N, ly.h2x, P, q, st, rel ? e->rel_list.as<int>() : nullptr, rel ? e->n_rel.as<int>() : nullptr);
+    }
     {
       Prof pr(e, st, EV_EDGE_MLP);
       edge_mlp(e, P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st,
@@ -693,7 +707,9 @@ extern "C" int tdiff_get_node_pos(tdiff_engine* e, float* d_x, void* stream) {
 // ---------------------------------------------------------------------------------------------- sampling loop
 namespace {
 void run_step(tdiff_engine* e, cudaStream_t st, const TdStepArgs& base) {
+  e->restrict_last = true;
   run_forward(e, st, 0);
+  e->restrict_last = false;
   TdStepArgs A = base;
   A.xm_final = e->final_buf ? e->xm1.as<float4>() : e->xm0.as<float4>();
   td_launch_step_epilogue(A, st);

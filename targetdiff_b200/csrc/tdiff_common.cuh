@@ -113,7 +113,7 @@ __device__ __forceinline__ void tile_gemm_128(const float* __restrict__ As, cons
 void td_launch_knn(const float4* xm, const int* node_ptr, int n_graphs, int max_nodes_per_graph, int k, int* src, cudaStream_t st);
 void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int have_prev, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
-                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, cudaStream_t st);
+                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, unsigned char* rel_flag, cudaStream_t st);
 void td_launch_protein_embed(const float* feat, int n_protein, int fdim, const float* w, const float* b, const int* prot_node,
                              float* h0, cudaStream_t st);
 void td_launch_init_h(const float* h0, const float4* xm, const int* lig_v, const int* node_lig, const float* wl_t, const float* bl,
@@ -130,9 +130,10 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
                            int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
                            const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const int* slow_list, const int* n_slow,
                            const float* qnode, float* out, const float* agg_logits, const float* agg_e_w, float* agg_h, int agg_n_nodes,
-                           int sm_count, cudaStream_t st);
+                           const int* d_n_dst, int sm_count, cudaStream_t st);
 void td_launch_rows_tc(int mode, const float* in, int ldi, int in_off, long long n_rows, TdMlp m, const unsigned char* w_image, int pieces, float* out,
-                       int ldo, int nblocks, int sm_count, cudaStream_t st);
+                       int ldo, int nblocks, const int* row_list, const int* d_n_rows, int sm_count, cudaStream_t st);
+void td_launch_rel_compact(const unsigned char* flag, int n_nodes, int* rel_list, int* n_rel, cudaStream_t st);
 void td_launch_aggregate_h(const float* kbuf, const float* vbuf, const float* e_w, const int* src, const float* q, const float* h_in,
                            float* h_out, int n_nodes, int k, cudaStream_t st);
 void td_launch_aggregate_x(const float* kbuf, const float* v16, const float* e_w, const int* src, const float* q, const float4* xm_in,

@@ -172,3 +172,21 @@ def test_sample_diffusion_ligand_on_gpu_prior_sizes():
     seed_all(2021)
     out2 = sample_diffusion_ligand(model, data, num_samples=5, batch_size=3, device=DEV, num_steps=4, sample_num_atoms='prior')
     assert all(np.array_equal(a, c) for a, c in zip(out[0], out2[0]))            # seed_all reproduces the run
+
+
+def test_relevant_node_restriction_is_exact(monkeypatch):
+    """The sampling loop evaluates the h2x node-side GEMMs and the last layer's x2h only for ligand atoms and their neighbours
+    (the only rows that reach the outputs, reference models/uni_transformer.py:197-206 + molopt_score_model.py:383-401).
+    Rows are independent, so the restricted chain must be bit-identical to the unrestricted one."""
+    b = synth.make_batch(5, 6, n_protein=250, ligand_sizes=[20, 7, 33, 1, 25, 12])
+    S = 12
+    pn, vu = synth.make_tape(11, S, int(b['init_ligand_pos'].shape[0]))
+    res = []
+    for off in ('', '1'):
+        if off:
+            monkeypatch.setenv('TDIFF_NO_RESTRICT', off)
+        model, _ = _model(3)
+        res.append(model.sample_diffusion(*_args(b), num_steps=S, center_pos_mode='protein', noise_tape=(pn, vu)))
+    assert torch.equal(res[0]['pos'], res[1]['pos']) and torch.equal(res[0]['v'], res[1]['v'])
+    assert torch.equal(torch.stack(res[0]['v0_traj']), torch.stack(res[1]['v0_traj']))
+    assert torch.equal(torch.stack(res[0]['pos_traj']), torch.stack(res[1]['pos_traj']))

@@ -18,6 +18,8 @@ SOURCES = ['engine.cu', 'knn.cu', 'edge_const.cu', 'node_ops.cu', 'edge_mlp.cu',
 HEADERS = ['tdiff_common.cuh', 'sampler.cuh', os.path.join('..', '..', 'include', 'tdiff.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
               '-Xcompiler', '-fvisibility=hidden', '-Xptxas', '-v']
+# developer switch, e.g. TDIFF_NVCC_EXTRA=-DTDIFF_V3_TIMELINE (clock64 timeline stamps in edge_mlp_v3, see tools/v3_timeline.py)
+NVCC_FLAGS += os.environ.get('TDIFF_NVCC_EXTRA', '').split()
 
 
 def nvcc_path():

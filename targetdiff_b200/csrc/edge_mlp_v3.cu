@@ -26,6 +26,7 @@
 // Shared memory (226 KB): W2 pieces 64 KB | A pieces 64 KB | S fp32 64 KB | G pieces 16 KB | Tab3 pieces 16 KB | 2 KB misc.
 // TMEM 512 columns: D[2] at 0/128, Dpre[2] at 256/384.  bf16 split: 2 pieces / 3 products (see edge_mlp_tc.cu).
 #include <stdio.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -33,8 +34,10 @@
 
 namespace v3 {
 
+// Warp roles (warpgroup-aligned for setmaxnreg): 0-3 epilogue of accumulator columns 0-63, 4-7 epilogue of columns 64-127 (warp w
+// reads TMEM lanes 32*(w%4) ..), 8-11 gather (11 also issues the MMAs), 12-27 row threads.
 constexpr int kThreads = 28 * 32;
-constexpr int kEpiWarps = 4, kMmaWarp = 4, kGatherWarp0 = 8, kGatherWarps = 4, kRowWarp0 = 12, kRowWarps = 16;
+constexpr int kEpiWarps = 8, kGatherWarp0 = 8, kGatherWarps = 4, kMmaWarp = 11, kRowWarp0 = 12, kRowWarps = 16;
 constexpr int kPiece = 128 * 128 * 2;      // bf16 piece of a 128x128 tile (two K-halves of 128 rows x 128 B)
 constexpr int kAtom = 128 * 128;           // 128 rows x 128 B
 constexpr int kGPiece = 128 * 64;          // bf16 piece of a 128 x 32 tile (SWIZZLE_64B, 64 B rows)
@@ -145,6 +148,16 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// line prefetch into L1 (the kernel's own gathers are L2-only cp.async copies, so the small L1 is left to these broadcast rows)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// 32-byte streaming load (one full sector per thread, not kept in L1): row-strided per-thread reads would otherwise pull whole
+// 128-byte lines through a 28 KB L1 once per 16-byte piece
+__device__ __forceinline__ void ldg256_stream(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -170,41 +183,28 @@ struct AggArgs {
   const float* e_w;      // [E]
   float* h;              // [N,128] node features, updated in place (row of a destination is touched by one warp only)
   int n_nodes;
+  int key_softmax;       // key launch (k == 32): write softmax(logits) * e_w instead of the raw logits; the value launch then reads weights
 };
 
-// Reduce 16 per-lane values over the 32 lanes of a warp with a transposing butterfly: 15 + 1 shuffles instead of 16 x 5.
-// On return lanes l and l^16 both hold the total (sum or max) of element (l & 15).
-template <bool MAX>
-__device__ __forceinline__ float warp_transpose_reduce16(float (&t)[16], int lane) {
+// Reduce N (8 or 16) per-lane values over the 32 lanes of a warp with a transposing butterfly: N - 1 + log2(32 / N) shuffles instead
+// of 5 N.  On return lane l holds the total (sum or max) of element (l & (N - 1)).
+template <int N, bool MAX>
+__device__ __forceinline__ float warp_transpose_reduce(float (&t)[N], int lane) {
   auto op = [](float a, float b) { return MAX ? fmaxf(a, b) : a + b; };
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool up = lane & 8;
-    const float send = up ? t[i] : t[i + 8];
-    const float keep = up ? t[i + 8] : t[i];
-    t[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-  }
+  for (int h = N / 2; h >= 1; h >>= 1) {
+    const bool up = lane & h;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = lane & 4;
-    const float send = up ? t[i] : t[i + 4];
-    const float keep = up ? t[i + 4] : t[i];
-    t[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? t[i] : t[i + h];
+      const float keep = up ? t[i + h] : t[i];
+      t[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, h));
+    }
   }
+  float r = t[0];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool up = lane & 2;
-    const float send = up ? t[i] : t[i + 2];
-    const float keep = up ? t[i + 2] : t[i];
-    t[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, 2));
-  }
-  {
-    const bool up = lane & 1;
-    const float send = up ? t[0] : t[1];
-    const float keep = up ? t[1] : t[0];
-    t[0] = op(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-  }
-  return op(t[0], __shfl_xor_sync(0xffffffffu, t[0], 16));
+  for (int m = N; m < 32; m <<= 1) r = op(r, __shfl_xor_sync(0xffffffffu, r, m));
+  return r;
 }
 // 8 consecutive values -> two bf16 pieces (16 bytes each); residual of the first piece is exact in fp32
 __device__ __forceinline__ void split8_store(uint32_t addr_p0, uint32_t addr_p1, const float (&y)[8]) {
@@ -212,11 +212,33 @@ __device__ __forceinline__ void split8_store(uint32_t addr_p0, uint32_t addr_p1,
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     h[i] = cvt_bf16x2(y[2 * i + 1], y[2 * i]);
-    const float r0 = y[2 * i] - __uint_as_float(h[i] << 16), r1 = y[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+    float r0, r1;
+    upk2(sub2(pk2(y[2 * i], y[2 * i + 1]), pk2(__uint_as_float(h[i] << 16), __uint_as_float(h[i] & 0xffff0000u))), r0, r1);
     l[i] = cvt_bf16x2(r1, r0);
   }
   sts128(addr_p0, h[0], h[1], h[2], h[3]);
   sts128(addr_p1, l[0], l[1], l[2], l[3]);
+}
+
+// LayerNorm affine + ReLU + bf16 split + store of one row's feature quarter QQ into the activation tile (features 32*QQ + 8*c ..
+// -> K-half QQ/2, chunk 4*(QQ&1)+c).  QQ is a template parameter so that g / b are immediate constant-bank operands.
+template <int QQ>
+__device__ __forceinline__ void affine_relu_store(const f2 (&x)[16], float rstd, const LnParams& lp, uint32_t sA, int r) {
+  const f2 rstd2 = pk2(rstd, rstd);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = 32 * QQ + 8 * c + 2 * i;
+      const f2 a2 = mul2(rstd2, pk2(lp.g[f], lp.g[f + 1]));
+      upk2(fma2(x[4 * c + i], a2, pk2(lp.b[f], lp.b[f + 1])), y[2 * i], y[2 * i + 1]);
+      y[2 * i] = fmaxf(y[2 * i], 0.f);
+      y[2 * i + 1] = fmaxf(y[2 * i + 1], 0.f);
+    }
+    const uint32_t addr = sA + (uint32_t)(QQ >> 1) * kAtom + (uint32_t)r * 128u + (uint32_t)(((4 * (QQ & 1) + c) ^ (r & 7)) << 4);
+    split8_store(addr, addr + kPiece, y);
+  }
 }
 
 }  // namespace v3
@@ -238,7 +260,16 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
   auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
   // debug timeline: role `ro`, event `ev` of local tile `t` (CTA 0, first 16 tiles) -> ts[(t*4 + ro)*8 + ev]
   auto stamp = [&](int ro, long long t, int ev) {
+#ifdef TDIFF_V3_TIMELINE
     if (ts && blockIdx.x == 0 && t < 16 && (threadIdx.x & 31) == 0) ts[(t * 4 + ro) * 8 + ev] = clock64();
+#endif
+  };
+  // row -> (destination slot, neighbour slot): k is a power of two for every shipped configuration but 48
+  const int kshift = (k & (k - 1)) == 0 ? __ffs(k) - 1 : -1;
+  auto row_dst = [&](long long idx, int& j) -> unsigned {
+    const unsigned a = kshift >= 0 ? (unsigned)idx >> kshift : (unsigned)idx / (unsigned)k;
+    j = (int)((unsigned)idx - a * (unsigned)k);
+    return a;
   };
 
   if ((sbase & 1023u) != 0) __trap();            // SWIZZLE_128B atoms need a 1024-byte aligned window
@@ -286,14 +317,15 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
     float mu[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) mu[i] = offsets[5 * qq + i];
+    const float coeff2 = coeff * 1.4426950408889634f;
     // metadata of this thread's row in tile `t` (s < 0: absent edge / beyond n_rows)
     auto load_md = [&](long long t, int& s_, int& ty_, int& dst_, float& dist_) {
       s_ = -1; ty_ = 0; dst_ = 0; dist_ = 0.f;
       if (t < my_tiles) {
         const long long idx = (blockIdx.x + t * (long long)gridDim.x) * 128 + r;
         if (idx < n_rows) {
-          const unsigned a = (unsigned)idx / (unsigned)k;
-          const int j = (int)((unsigned)idx - a * (unsigned)k);
+          int j;
+          const unsigned a = row_dst(idx, j);
           dst_ = row_nodes ? row_nodes[a] : (int)a;
           const size_t e = (size_t)dst_ * k + j;
           s_ = src[e]; ty_ = etype[e]; dist_ = dist_arr[e];
@@ -308,7 +340,7 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const float t = dist_ - mu[i];
-        gv[i] = t3 ? expf(coeff * (t * t)) : 0.0f;
+        gv[i] = t3 ? ex2_approx(coeff2 * (t * t)) : 0.0f;          // exp(coeff t^2); the bf16 split below keeps 16 bits of it
       }
       gv[5] = (t3 && qq == 3) ? 1.0f : 0.0f;
       gv[6] = gv[7] = 0.0f;
@@ -346,10 +378,13 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       }
       if (valid && t0 != 3 && !(dbg & 8)) {
         const float* tr = tslow + (size_t)((blockIdx.x + it * (long long)gridDim.x) * 128 + r) * TD_H + 32 * qq;
+        float tv[4][8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(tr + 4 * c));
-          x[2 * c] = add2(x[2 * c], pk2(v.x, v.y)); x[2 * c + 1] = add2(x[2 * c + 1], pk2(v.z, v.w));
+        for (int c = 0; c < 4; ++c) ldg256_stream(tr + 8 * c, tv[c]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) x[4 * c + i] = add2(x[4 * c + i], pk2(tv[c][2 * i], tv[c][2 * i + 1]));
         }
       }
       __syncwarp();
@@ -375,6 +410,11 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       if (it + 1 < my_tiles) write_g(s1, t1, dist1);
       s0 = s1; t0 = t1; d0 = d1; dist0 = dist1;
       load_md(it + 2, s1, t1, d1, dist1);
+      // the next tile's destination row quarter (and precomputed gaussian row of the rare types) -> L1 while this tile is normalised
+      if (s0 >= 0) {
+        prefetch_l1(P + (size_t)d0 * TD_NPROJ + m.offA + 32 * qq);
+        if (t0 != 3) prefetch_l2(tslow + (size_t)((blockIdx.x + (it + 1) * (long long)gridDim.x) * 128 + r) * TD_H + 32 * qq);
+      }
       if (rwp == 0) stamp(0, it, 3);
       // ---- LayerNorm over the 128 features of the row: 4 threads (feature quarters) exchange partial sums through smem
       f2 sa = add2(x[0], x[1]), sb = add2(x[2], x[3]), sc = add2(x[4], x[5]), sd = add2(x[6], x[7]);
@@ -397,25 +437,25 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       named_bar_sync(1 + q, 128);
       const float var = ((lds32f(xslot) + lds32f(xslot + 512u)) + (lds32f(xslot + 1024u) + lds32f(xslot + 1536u))) * (1.0f / 128.0f);
       named_bar_sync(1 + q, 128);                 // slots are rewritten early in the next tile
-      const float rstd = valid ? 1.0f / sqrtf(var + 1e-5f) : 0.0f;
-      const f2 rstd2 = pk2(rstd, rstd);
+      const float rstd = rsqrtf(var + 1e-5f);
       // ---- affine + ReLU, bf16 split, store into the activation tile: features 32*qq + 8*c .. -> K-half qq/2, chunk 4*(qq&1)+c
       if (rwp == 0) stamp(0, it, 4);
       mbar_wait(bar(B_A_EMPTY), ph ^ 1u);
       if (rwp == 0) stamp(0, it, 5);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float y[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int f = 32 * qq + 8 * c + 2 * i;
-          const f2 a2 = mul2(rstd2, pk2(lp.g[f], lp.g[f + 1]));
-          upk2(fma2(x[4 * c + i], a2, pk2(lp.b[f], lp.b[f + 1])), y[2 * i], y[2 * i + 1]);
-          y[2 * i] = valid ? fmaxf(y[2 * i], 0.f) : 0.f;
-          y[2 * i + 1] = valid ? fmaxf(y[2 * i + 1], 0.f) : 0.f;
+      if (valid) {
+        switch (qq) {                               // warp-uniform
+          case 0: affine_relu_store<0>(x, rstd, lp, sA, r); break;
+          case 1: affine_relu_store<1>(x, rstd, lp, sA, r); break;
+          case 2: affine_relu_store<2>(x, rstd, lp, sA, r); break;
+          default: affine_relu_store<3>(x, rstd, lp, sA, r); break;
         }
-        const uint32_t addr = sA + (uint32_t)(qq >> 1) * kAtom + (uint32_t)r * 128u + (uint32_t)(((4 * (qq & 1) + c) ^ (r & 7)) << 4);
-        split8_store(addr, addr + kPiece, y);
+      } else {                                      // absent edge / row beyond the end: zero activation row
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t addr = sA + (uint32_t)(qq >> 1) * kAtom + (uint32_t)r * 128u + (uint32_t)(((4 * (qq & 1) + c) ^ (r & 7)) << 4);
+          sts128(addr, 0u, 0u, 0u, 0u);
+          sts128(addr + kPiece, 0u, 0u, 0u, 0u);
+        }
       }
       fence_proxy_async();
       __syncwarp();
@@ -423,52 +463,27 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       if (rwp == 0) stamp(0, it, 6);
     }
   } else if (warp >= kGatherWarp0) {
-    // ================================================================= gather warps (lane = 4 features), 16 rows each
-    reg_dec<40>();
+    // ================================================================= gather warps (lane = 4 features), 32 rows each; the last one
+    //                                                                   also issues the MMAs (one thread) between its copies
+    reg_dec<40>();     // register budget: 256*72 (epilogue, launch value) + 128*40 (gather / MMA) + 512*80 (rows) = 64512 = 896 x 72
     const int gw = warp - kGatherWarp0;
+    const bool mma_warp = warp == kMmaWarp;
     const int atom = lane >> 3, ch = lane & 7;
-    // metadata of row 32*gw + lane of tile t
-    auto load_md = [&](long long t, int& s_, int& ty_, float& dist_) {
-      s_ = -1; ty_ = 3; dist_ = 0.f;
+    // source node of row 32*gw + lane of tile t
+    auto load_md = [&](long long t) -> int {
+      int s_ = -1;
       if (t < my_tiles) {
         const long long idx = (blockIdx.x + t * (long long)gridDim.x) * 128 + 32 * gw + lane;
         if (idx < n_rows) {
-          const unsigned a = (unsigned)idx / (unsigned)k;
-          const int j = (int)((unsigned)idx - a * (unsigned)k);
+          int j;
+          const unsigned a = row_dst(idx, j);
           const int dst = row_nodes ? row_nodes[a] : (int)a;
-          const size_t e = (size_t)dst * k + j;
-          s_ = src[e]; ty_ = etype[e]; dist_ = dist_arr[e];
+          s_ = src[(size_t)dst * k + j];
         }
       }
+      return s_;
     };
-    int s0, t0, s1, t1;
-    float dist0, dist1;
-    load_md(0, s0, t0, dist0);
-    for (long long it = 0; it < my_tiles; ++it) {
-      load_md(it + 1, s1, t1, dist1);                      // next tile's metadata lands while this tile's rows are copied
-      if (gw == 0) stamp(1, it, 0);
-      mbar_wait(bar(B_S_EMPTY), (uint32_t)((it & 1) ^ 1));
-      if (gw == 0) stamp(1, it, 1);
-      // ---- P[src_row, offB + 4*lane ..] -> S, 32 rows x 512 B per warp, asynchronously (no registers, L2 -> shared)
-#pragma unroll 8
-      for (int rr = 0; rr < 32; ++rr) {
-        const int row = 32 * gw + rr;
-        const int sr = __shfl_sync(0xffffffffu, s0, rr);
-        const uint32_t dsta = sS + (uint32_t)atom * kAtom + (uint32_t)row * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
-        if (sr >= 0 && !(dbg & 2)) cp_async16(dsta, P + (size_t)sr * TD_NPROJ + m.offB + 4 * lane);
-        else sts128f(dsta, make_float4(0.f, 0.f, 0.f, 0.f));
-      }
-      cp_async_wait_all();
-      if (gw == 0) stamp(1, it, 2);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_S_FULL));
-      if (gw == 0) stamp(1, it, 3);
-      s0 = s1; t0 = t1; dist0 = dist1;
-    }
-  } else if (warp >= kMmaWarp) {
-    // ================================================================= MMA issuer (one thread of warp 4; warps 5-7 idle)
-    reg_dec<56>();
-    // Dpre[t&1] = G(t) . Tab3^T   (K = 32: two K=16 instructions per product term); issued one tile ahead of the main MMA
+    // Dpre[t&1] = G(t) . Tab3^T   (K = 32: two K=16 instructions per product term)
     auto issue_pre = [&](long long t) {
       stamp(2, t, 0);
       mbar_wait(bar(B_G_FULL), (uint32_t)(t & 1));
@@ -490,16 +505,14 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       }
       __syncwarp();
     };
-    if (warp == kMmaWarp && my_tiles > 0) issue_pre(0);
-    for (long long it = 0; warp == kMmaWarp && it < my_tiles; ++it) {
-      const uint32_t ph = (uint32_t)(it & 1), ph2 = (uint32_t)((it >> 1) & 1);
-      if (it + 1 < my_tiles) issue_pre(it + 1);
-      // D[ph] = A . W2^T
-      stamp(2, it, 2);
+    // D[t&1] = A(t) . W2^T
+    auto issue_main = [&](long long t) {
+      const uint32_t ph = (uint32_t)(t & 1), ph2 = (uint32_t)((t >> 1) & 1);
+      stamp(2, t, 2);
       mbar_wait_relaxed(bar(B_D_EMPTY0 + (int)ph), ph2 ^ 1u);
-      stamp(2, it, 3);
+      stamp(2, t, 3);
       mbar_wait(bar(B_A_FULL), ph);
-      stamp(2, it, 4);
+      stamp(2, t, 4);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t d_addr = tmem_base + ph * 128u;
@@ -518,146 +531,204 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
         umma_commit(bar(B_D_FULL0 + (int)ph));
       }
       __syncwarp();
-      stamp(2, it, 5);
+      stamp(2, t, 5);
+    };
+    int s0 = load_md(0);
+    // iteration `it`: copy S(it) (overlaps the row threads' work on tile it-1), then Dpre(it), then the main MMA of tile it-1
+    // (its operands become ready when the row threads finish tile it-1, i.e. just before they need S(it))
+    for (long long it = 0; it <= my_tiles; ++it) {
+      if (it < my_tiles) {
+        const int s1 = load_md(it + 1);                      // next tile's metadata lands while this tile's rows are copied
+        if (gw == 0) stamp(1, it, 0);
+        mbar_wait(bar(B_S_EMPTY), (uint32_t)((it & 1) ^ 1));
+        if (gw == 0) stamp(1, it, 1);
+        // ---- P[src_row, offB + 4*lane ..] -> S, 32 rows x 512 B per warp, asynchronously (no registers, L2 -> shared)
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          const int row = 32 * gw + rr;
+          const int sr = __shfl_sync(0xffffffffu, s0, rr);
+          const uint32_t dsta = sS + (uint32_t)atom * kAtom + (uint32_t)row * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+          if (sr >= 0 && !(dbg & 2)) cp_async16(dsta, P + (size_t)sr * TD_NPROJ + m.offB + 4 * lane);
+          else sts128f(dsta, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        cp_async_wait_all();
+        if (gw == 0) stamp(1, it, 2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_S_FULL));
+        if (gw == 0) stamp(1, it, 3);
+        s0 = s1;
+        if (mma_warp) issue_pre(it);
+      }
+      if (mma_warp && it >= 1) issue_main(it - 1);
     }
   } else {
-    // ================================================================= epilogue (warps 0..3 <-> TMEM lanes 32w..32w+31)
-    reg_inc<88>();     // register budget: 128*88 + 128*56 + 128*40 + 512*80 = 64512 = 896 threads x 72
-    for (long long it = 0; it < my_tiles; ++it) {
-      const long long tile = blockIdx.x + it * gridDim.x;
-      const uint32_t ph = (uint32_t)(it & 1), ph2 = (uint32_t)((it >> 1) & 1);
-      if (warp == 0) stamp(3, it, 0);
-      // fused aggregation (value launch, k == 32): everything that does not depend on the accumulator is fetched before waiting for it
-      const bool do_agg = NOUT == 128 && qnode == nullptr && agg.logits != nullptr;
-      const long long dslot = tile * 4 + warp;                        // k == 32: destination index of this warp's 32 rows
-      const bool active = do_agg && dslot * 32 < n_rows;              // warp-uniform
-      const long long dnode = (active && row_nodes) ? row_nodes[dslot] : dslot;
-      bool valid_e = false;
-      float w[16], hin[8], ew = 0.f;
-      if (do_agg) {
-        const long long e = dnode * 32 + lane;                         // slot (src, e_w); logits are indexed by the launch's row
-        valid_e = active && src[e] >= 0;
-        if (valid_e) {
-          ew = agg.e_w[e];
+    // ================================================================= epilogue: warp w <-> TMEM lanes 32 (w%4) .., columns 64 (w/4) ..
+    const int eq = warp & 3;
+    auto epilogue = [&](auto HALF_) {
+      constexpr int HALF = decltype(HALF_)::value;
+      for (long long it = 0; it < my_tiles; ++it) {
+        const long long tile = blockIdx.x + it * gridDim.x;
+        const uint32_t ph = (uint32_t)(it & 1), ph2 = (uint32_t)((it >> 1) & 1);
+        if (warp == 0) stamp(3, it, 0);
+        const uint32_t tbase = tmem_base + ((uint32_t)(eq * 32) << 16) + ph * 128u + (uint32_t)(64 * HALF);
+        // fused aggregation (value launch, k == 32): everything that does not depend on the accumulator is fetched before waiting for it
+        const bool do_agg = NOUT == 128 && qnode == nullptr && agg.logits != nullptr;
+        const bool key_sm = NOUT == 128 && qnode != nullptr && agg.key_softmax;    // key launch, k == 32: softmax in this epilogue
+        const long long idx = tile * 128 + eq * 32 + lane;
+        const long long dslot = tile * 4 + eq;                          // k == 32: destination index of this warp's 32 rows
+        const bool active = do_agg && dslot * 32 < n_rows;              // warp-uniform
+        const long long dnode = (active && row_nodes) ? row_nodes[dslot] : dslot;
+        float w[8], hin[4], ew = 0.f;
+        bool valid_e = false;
+        int dst = 0;
+        if (do_agg) {
+          // attention weights alpha * e_w of this destination's 32 edges, heads 8 HALF .. (written by the key launch's epilogue)
+          if (active) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(agg.logits + (size_t)(dslot * 32 + lane) * TD_HEADS + 4 * i));
-            w[4 * i] = t4.x; w[4 * i + 1] = t4.y; w[4 * i + 2] = t4.z; w[4 * i + 3] = t4.w;
+            for (int i = 0; i < 2; ++i) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(agg.logits + (size_t)idx * TD_HEADS + 8 * HALF + 4 * i));
+              w[4 * i] = t4.x; w[4 * i + 1] = t4.y; w[4 * i + 2] = t4.z; w[4 * i + 3] = t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = 0.0f;
           }
-        } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) w[i] = -INFINITY;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) hin[j] = (active && lane < 16) ? agg.h[(size_t)dnode * TD_H + 16 * j + lane] : 0.0f;
-      }
-      mbar_wait_relaxed(bar(B_D_FULL0 + (int)ph), ph2);
-      if (warp == 0) stamp(3, it, 1);
-      tc_fence_after();
-      const long long idx = tile * 128 + warp * 32 + lane;
-      if (NOUT == 16) {
-        // ---- xv: out[row, 0:16] = D[:, 0:16] + b2
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + ph * 128u, v);
-        if (idx < n_rows && !(dbg & 1)) {
-          float* orow = out + (size_t)idx * 16;
-          stg256(orow, __uint_as_float(v[0]) + lp.b2[0], __uint_as_float(v[1]) + lp.b2[1], __uint_as_float(v[2]) + lp.b2[2],
-                 __uint_as_float(v[3]) + lp.b2[3], __uint_as_float(v[4]) + lp.b2[4], __uint_as_float(v[5]) + lp.b2[5],
-                 __uint_as_float(v[6]) + lp.b2[6], __uint_as_float(v[7]) + lp.b2[7]);
-          stg256(orow + 8, __uint_as_float(v[8]) + lp.b2[8], __uint_as_float(v[9]) + lp.b2[9], __uint_as_float(v[10]) + lp.b2[10],
-                 __uint_as_float(v[11]) + lp.b2[11], __uint_as_float(v[12]) + lp.b2[12], __uint_as_float(v[13]) + lp.b2[13],
-                 __uint_as_float(v[14]) + lp.b2[14], __uint_as_float(v[15]) + lp.b2[15]);
-        }
-      } else if (do_agg) {
-        // ---- value MLP with the attention aggregation fused in: this warp's 32 rows are the edges of destination 4*tile + warp
-        {
-          // softmax over the 32 edges for the 16 heads: head hh's max / sum end up in lanes hh and hh+16, then are broadcast
-          float tmp[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) tmp[i] = w[i];
-          const float mx_mine = warp_transpose_reduce16<true>(tmp, lane);
-#pragma unroll
-          for (int hh = 0; hh < 16; ++hh) {
-            const float mx = __shfl_sync(0xffffffffu, mx_mine, hh);
-            w[hh] = valid_e ? expf(w[hh] - mx) : 0.0f;
-            tmp[hh] = w[hh];
+          for (int j = 0; j < 4; ++j) hin[j] = (active && lane < 16) ? agg.h[(size_t)dnode * TD_H + 64 * HALF + 16 * j + lane] : 0.0f;
+          // next tile: weights and destination row -> L1
+          const long long nslot = dslot + 4 * (long long)gridDim.x;
+          if (it + 1 < my_tiles && nslot * 32 < n_rows) {
+            prefetch_l1(agg.logits + (size_t)(idx + 128 * (long long)gridDim.x) * TD_HEADS + 8 * HALF);
+            if (lane < 2) prefetch_l1(agg.h + (size_t)(row_nodes ? row_nodes[nslot] : nslot) * TD_H + 64 * HALF + 32 * lane);
           }
-          const float l_mine = warp_transpose_reduce16<false>(tmp, lane);
-          const float inv_mine = l_mine > 0.0f ? 1.0f / l_mine : 0.0f;
-#pragma unroll
-          for (int hh = 0; hh < 16; ++hh) w[hh] = w[hh] * ew * __shfl_sync(0xffffffffu, inv_mine, hh);      // alpha * e_w
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c0 = 16 * j;
-          uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + ph * 128u + (uint32_t)c0, v);
-          float t[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) t[i] = w[c0 / 8 + i / 8] * (__uint_as_float(v[i]) + lp.b2[c0 + i]);
-          const float tot = warp_transpose_reduce16<false>(t, lane);
-          if (active && lane < 16 && !(dbg & 1)) agg.h[(size_t)dnode * TD_H + c0 + lane] = hin[j] + tot;
-        }
-      } else if (qnode == nullptr) {
-        // ---- value MLPs: out[row, 0:128] = D + b2
-        float* orow = out + (size_t)idx * 128;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + ph * 128u + (uint32_t)c0, v);
-          if (idx < n_rows && !(dbg & 1)) {
-#pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-              const float* bb = lp.b2 + c0 + c;
-              stg256(orow + c0 + c, __uint_as_float(v[c]) + bb[0], __uint_as_float(v[c + 1]) + bb[1], __uint_as_float(v[c + 2]) + bb[2],
-                     __uint_as_float(v[c + 3]) + bb[3], __uint_as_float(v[c + 4]) + bb[4], __uint_as_float(v[c + 5]) + bb[5],
-                     __uint_as_float(v[c + 6]) + bb[6], __uint_as_float(v[c + 7]) + bb[7]);
+        } else if (NOUT == 128 && qnode != nullptr) {
+          if (idx < n_rows) {
+            int j;
+            const unsigned a = row_dst(idx, j);
+            dst = row_nodes ? row_nodes[a] : (int)a;
+            if (key_sm) {
+              const size_t e = (size_t)dst * k + j;
+              valid_e = src[e] >= 0;
+              ew = agg.e_w[e];
             }
           }
-        }
-      } else {
-        // ---- key MLPs: the keys never leave the SM.  out[row, 0:16] = attention logits  sum_d q[dst, 8h+d] * k[row, 8h+d] / sqrt(8)
-        //      (reference models/uni_transformer.py:73,135); thread = edge row, q row of the destination read as broadcast loads.
-        int dst = 0;
-        if (idx < n_rows) {
-          const unsigned a = (unsigned)idx / (unsigned)k;
-          dst = row_nodes ? row_nodes[a] : (int)a;
-        }
-        const float* qrow = qnode + (size_t)dst * TD_H;
-        float lg[16];
-#pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          float4 qv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) qv[i] = __ldg(reinterpret_cast<const float4*>(qrow + c0 + 4 * i));
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + ph * 128u + (uint32_t)c0, v);
-#pragma unroll
-          for (int hh = 0; hh < 4; ++hh) {
-            const float* bb = lp.b2 + c0 + 8 * hh;
-            const float4 qa = qv[2 * hh], qb = qv[2 * hh + 1];
-            float s = (__uint_as_float(v[8 * hh]) + bb[0]) * qa.x;
-            s = fmaf(__uint_as_float(v[8 * hh + 1]) + bb[1], qa.y, s);
-            s = fmaf(__uint_as_float(v[8 * hh + 2]) + bb[2], qa.z, s);
-            s = fmaf(__uint_as_float(v[8 * hh + 3]) + bb[3], qa.w, s);
-            s = fmaf(__uint_as_float(v[8 * hh + 4]) + bb[4], qb.x, s);
-            s = fmaf(__uint_as_float(v[8 * hh + 5]) + bb[5], qb.y, s);
-            s = fmaf(__uint_as_float(v[8 * hh + 6]) + bb[6], qb.z, s);
-            s = fmaf(__uint_as_float(v[8 * hh + 7]) + bb[7], qb.w, s);
-            lg[c0 / 8 + hh] = s * 0.35355339059327373f;          // 1/sqrt(8)
+          // next tile's query half row (2 lines per destination; the 32 rows of a warp share it when k == 32) -> L1
+          const long long nidx = idx + 128 * (long long)gridDim.x;
+          if (it + 1 < my_tiles && nidx < n_rows && (lane & 15) == 0) {
+            int j;
+            const unsigned a = row_dst(nidx, j);
+            prefetch_l1(qnode + (size_t)(row_nodes ? row_nodes[a] : (int)a) * TD_H + 64 * HALF + 2 * lane);
           }
         }
-        if (idx < n_rows && !(dbg & 1)) {
-          float* orow = out + (size_t)idx * TD_HEADS;
-          stg256(orow, lg[0], lg[1], lg[2], lg[3], lg[4], lg[5], lg[6], lg[7]);
-          stg256(orow + 8, lg[8], lg[9], lg[10], lg[11], lg[12], lg[13], lg[14], lg[15]);
+        mbar_wait_relaxed(bar(B_D_FULL0 + (int)ph), ph2);
+        if (warp == 0) stamp(3, it, 1);
+        tc_fence_after();
+        if (NOUT == 16) {
+          // ---- xv: out[row, 0:16] = D[:, 0:16] + b2   (first column half only)
+          if (HALF == 0) {
+            uint32_t v[16];
+            tmem_ld16(tbase, v);
+            if (idx < n_rows && !(dbg & 1)) {
+              float* orow = out + (size_t)idx * 16;
+              stg256(orow, __uint_as_float(v[0]) + lp.b2[0], __uint_as_float(v[1]) + lp.b2[1], __uint_as_float(v[2]) + lp.b2[2],
+                     __uint_as_float(v[3]) + lp.b2[3], __uint_as_float(v[4]) + lp.b2[4], __uint_as_float(v[5]) + lp.b2[5],
+                     __uint_as_float(v[6]) + lp.b2[6], __uint_as_float(v[7]) + lp.b2[7]);
+              stg256(orow + 8, __uint_as_float(v[8]) + lp.b2[8], __uint_as_float(v[9]) + lp.b2[9], __uint_as_float(v[10]) + lp.b2[10],
+                     __uint_as_float(v[11]) + lp.b2[11], __uint_as_float(v[12]) + lp.b2[12], __uint_as_float(v[13]) + lp.b2[13],
+                     __uint_as_float(v[14]) + lp.b2[14], __uint_as_float(v[15]) + lp.b2[15]);
+            }
+          }
+        } else if (do_agg) {
+          // ---- value MLP with the attention aggregation fused in: this warp's 32 rows are the edges of destination 4*tile + eq
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            constexpr int cb = 64 * HALF;
+            const int c0 = 16 * j;
+            uint32_t v[16];
+            tmem_ld16(tbase + (uint32_t)c0, v);
+            float t[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float wh = w[c0 / 8 + i / 4];
+              upk2(mul2(add2(pk2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
+                             pk2(lp.b2[cb + c0 + 2 * i], lp.b2[cb + c0 + 2 * i + 1])), pk2(wh, wh)), t[2 * i], t[2 * i + 1]);
+            }
+            const float tot = warp_transpose_reduce<16, false>(t, lane);
+            if (active && lane < 16 && !(dbg & 1)) agg.h[(size_t)dnode * TD_H + cb + c0 + lane] = hin[j] + tot;
+          }
+        } else if (qnode == nullptr) {
+          // ---- value MLPs: out[row, 64 HALF .. + 64] = D + b2
+          float* orow = out + (size_t)idx * 128 + 64 * HALF;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tbase + (uint32_t)c0, v);
+            if (idx < n_rows && !(dbg & 1)) {
+#pragma unroll
+              for (int c = 0; c < 32; c += 8) {
+                const float* bb = lp.b2 + 64 * HALF + c0 + c;
+                stg256(orow + c0 + c, __uint_as_float(v[c]) + bb[0], __uint_as_float(v[c + 1]) + bb[1], __uint_as_float(v[c + 2]) + bb[2],
+                       __uint_as_float(v[c + 3]) + bb[3], __uint_as_float(v[c + 4]) + bb[4], __uint_as_float(v[c + 5]) + bb[5],
+                       __uint_as_float(v[c + 6]) + bb[6], __uint_as_float(v[c + 7]) + bb[7]);
+              }
+            }
+          }
+        } else {
+          // ---- key MLPs: the keys never leave the SM.  out[row, 8 HALF .. + 8] = attention logits sum_d q[dst, 8h+d] k[row, 8h+d] / sqrt(8)
+          //      (reference models/uni_transformer.py:73,135); thread = edge row, q row of the destination read as broadcast loads.
+          const float* qrow = qnode + (size_t)dst * TD_H + 64 * HALF;
+          float lg[8];
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            float4 qv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qv[i] = __ldg(reinterpret_cast<const float4*>(qrow + c0 + 4 * i));
+            uint32_t v[16];
+            tmem_ld16(tbase + (uint32_t)c0, v);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const float* bb = lp.b2 + 64 * HALF + c0 + 8 * hh;
+              const float4 qa = qv[2 * hh], qb = qv[2 * hh + 1];
+              float sacc = (__uint_as_float(v[8 * hh]) + bb[0]) * qa.x;
+              sacc = fmaf(__uint_as_float(v[8 * hh + 1]) + bb[1], qa.y, sacc);
+              sacc = fmaf(__uint_as_float(v[8 * hh + 2]) + bb[2], qa.z, sacc);
+              sacc = fmaf(__uint_as_float(v[8 * hh + 3]) + bb[3], qa.w, sacc);
+              sacc = fmaf(__uint_as_float(v[8 * hh + 4]) + bb[4], qb.x, sacc);
+              sacc = fmaf(__uint_as_float(v[8 * hh + 5]) + bb[5], qb.y, sacc);
+              sacc = fmaf(__uint_as_float(v[8 * hh + 6]) + bb[6], qb.z, sacc);
+              sacc = fmaf(__uint_as_float(v[8 * hh + 7]) + bb[7], qb.w, sacc);
+              lg[c0 / 8 + hh] = sacc * 0.35355339059327373f;          // 1/sqrt(8)
+            }
+          }
+          if (key_sm) {
+            // softmax over the destination's 32 edges (= this warp's rows) for this warp's 8 heads, times the edge gate: the value
+            // launch's epilogue only has to weight and sum.  Head hh's max / sum end up in the lanes = hh (mod 8), then are broadcast.
+            float tmp[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tmp[i] = lg[i] = valid_e ? lg[i] * 1.4426950408889634f : -INFINITY;
+            const float mx_mine = warp_transpose_reduce<8, true>(tmp, lane);
+#pragma unroll
+            for (int hh = 0; hh < 8; ++hh) {
+              const float mx = __shfl_sync(0xffffffffu, mx_mine, hh);
+              lg[hh] = valid_e ? ex2_approx(lg[hh] - mx) : 0.0f;
+              tmp[hh] = lg[hh];
+            }
+            const float l_mine = warp_transpose_reduce<8, false>(tmp, lane);
+            const float inv_mine = l_mine > 0.0f ? 1.0f / l_mine : 0.0f;
+#pragma unroll
+            for (int hh = 0; hh < 8; ++hh) lg[hh] = lg[hh] * ew * __shfl_sync(0xffffffffu, inv_mine, hh);      // alpha * e_w
+          }
+          if (idx < n_rows && !(dbg & 1))
+            stg256(out + (size_t)idx * TD_HEADS + 8 * HALF, lg[0], lg[1], lg[2], lg[3], lg[4], lg[5], lg[6], lg[7]);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_D_EMPTY0 + (int)ph));
+        if (warp == 0) stamp(3, it, 2);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_D_EMPTY0 + (int)ph));
-      if (warp == 0) stamp(3, it, 2);
-    }
+    };
+    if (warp < 4) epilogue(std::integral_constant<int, 0>{});
+    else epilogue(std::integral_constant<int, 1>{});
   }
   // ---- teardown
   tc_fence_before();
@@ -745,7 +816,7 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
                            int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
                            const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const int* slow_list, const int* n_slow,
                            const float* qnode, float* out, const float* agg_logits, const float* agg_e_w, float* agg_h, int agg_n_nodes,
-                           const int* d_n_dst, int sm_count, cudaStream_t st) {
+                           const int* d_n_dst, int key_softmax, int sm_count, cudaStream_t st) {
   if (n_rows == 0) return;
   LnParams lp;
   memcpy(lp.g, h_ln_g, sizeof(lp.g));
@@ -767,7 +838,7 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
     edge_slow_kernel<<<(int)blocks, 256, 0, st>>>(src, etype, dist, row_nodes, n_rows, k, listed ? slow_list : nullptr, n_slow, d_n_dst, m.tab, offsets,
                                                   coeff, tslow);
   }
-  AggArgs agg = {agg_logits, agg_e_w, agg_h, agg_n_nodes};
+  AggArgs agg = {agg_logits, agg_e_w, agg_h, agg_n_nodes, (key_softmax && k == 32) ? 1 : 0};
   static int dbg = -1;
   static long long* d_ts = nullptr;
   if (dbg < 0) {

@@ -546,11 +546,11 @@ bool fused_logits(const tdiff_engine* e) { return e->mlp_mode == 2 && e->mlp_v3;
 void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
               long long n_rows, int K, const TdMlp& m, const float* offsets, float coeff, float* out, cudaStream_t st,
               const float* qnode = nullptr, const float* agg_logits = nullptr, float* agg_h = nullptr, int agg_n = 0,
-              const int* d_n_dst = nullptr) {
+              const int* d_n_dst = nullptr, int key_softmax = 0) {
   if (e->mlp_mode == 2 && e->mlp_v3 && m.w2_img && m.tab3_img)
     td_launch_edge_mlp_v3(P, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, m.tab3_img, offsets, coeff,
                           e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena), e->host_arena.data() + (m.b2 - e->arena), e->tslow.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), qnode, out, agg_logits, e->e_w.as<float>(), agg_h, agg_n,
-                          d_n_dst, e->sm_count, st);
+                          d_n_dst, key_softmax, e->sm_count, st);
   else if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
     td_launch_edge_mlp_tc(P, xm, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, e->mlp_mode, offsets, coeff, out, e->sm_count, st);
   else
@@ -604,7 +604,7 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     {
       Prof pr(e, st, EV_EDGE_MLP);
       edge_mlp(e, P, xm[cur], src, etype, rows, (long long)N * K, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st,
-               fused_logits(e) ? q : nullptr, nullptr, nullptr, 0, d_n);
+               fused_logits(e) ? q : nullptr, nullptr, nullptr, 0, d_n, fuse_agg ? 1 : 0);
       edge_mlp(e, P, xm[cur], src, etype, rows, (long long)N * K, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), st, nullptr,
                fuse_agg ? e->kbuf.as<float>() : nullptr, fuse_agg ? h : nullptr, N, d_n);
     }

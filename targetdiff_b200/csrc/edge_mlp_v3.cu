@@ -220,27 +220,6 @@ __device__ __forceinline__ void split8_store(uint32_t addr_p0, uint32_t addr_p1,
   sts128(addr_p1, l[0], l[1], l[2], l[3]);
 }
 
-// LayerNorm affine + ReLU + bf16 split + store of one row's feature quarter QQ into the activation tile (features 32*QQ + 8*c ..
-// -> K-half QQ/2, chunk 4*(QQ&1)+c).  QQ is a template parameter so that g / b are immediate constant-bank operands.
-template <int QQ>
-__device__ __forceinline__ void affine_relu_store(const f2 (&x)[16], float rstd, const LnParams& lp, uint32_t sA, int r) {
-  const f2 rstd2 = pk2(rstd, rstd);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    float y[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f = 32 * QQ + 8 * c + 2 * i;
-      const f2 a2 = mul2(rstd2, pk2(lp.g[f], lp.g[f + 1]));
-      upk2(fma2(x[4 * c + i], a2, pk2(lp.b[f], lp.b[f + 1])), y[2 * i], y[2 * i + 1]);
-      y[2 * i] = fmaxf(y[2 * i], 0.f);
-      y[2 * i + 1] = fmaxf(y[2 * i + 1], 0.f);
-    }
-    const uint32_t addr = sA + (uint32_t)(QQ >> 1) * kAtom + (uint32_t)r * 128u + (uint32_t)(((4 * (QQ & 1) + c) ^ (r & 7)) << 4);
-    split8_store(addr, addr + kPiece, y);
-  }
-}
-
 }  // namespace v3
 
 using namespace v3;
@@ -443,11 +422,24 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       mbar_wait(bar(B_A_EMPTY), ph ^ 1u);
       if (rwp == 0) stamp(0, it, 5);
       if (valid) {
-        switch (qq) {                               // warp-uniform
-          case 0: affine_relu_store<0>(x, rstd, lp, sA, r); break;
-          case 1: affine_relu_store<1>(x, rstd, lp, sA, r); break;
-          case 2: affine_relu_store<2>(x, rstd, lp, sA, r); break;
-          default: affine_relu_store<3>(x, rstd, lp, sA, r); break;
+        {
+          // one copy of this stage for all feature quarters (g / b through indexed constant loads): per-quarter instantiations
+          // cost more in instruction-cache misses and spills than they save
+          const f2 rstd2 = pk2(rstd, rstd);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int f = 32 * qq + 8 * c + 2 * i;
+              const f2 a2 = mul2(rstd2, pk2(lp.g[f], lp.g[f + 1]));
+              upk2(fma2(x[4 * c + i], a2, pk2(lp.b[f], lp.b[f + 1])), y[2 * i], y[2 * i + 1]);
+              y[2 * i] = fmaxf(y[2 * i], 0.f);
+              y[2 * i + 1] = fmaxf(y[2 * i + 1], 0.f);
+            }
+            const uint32_t addr = sA + (uint32_t)(qq >> 1) * kAtom + (uint32_t)r * 128u + (uint32_t)(((4 * (qq & 1) + c) ^ (r & 7)) << 4);
+            split8_store(addr, addr + kPiece, y);
+          }
         }
       } else {                                      // absent edge / row beyond the end: zero activation row
 #pragma unroll
@@ -564,8 +556,8 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
   } else {
     // ================================================================= epilogue: warp w <-> TMEM lanes 32 (w%4) .., columns 64 (w/4) ..
     const int eq = warp & 3;
-    auto epilogue = [&](auto HALF_) {
-      constexpr int HALF = decltype(HALF_)::value;
+    const int HALF = warp >> 2;                    // one code copy for both column halves (b2 through indexed constant loads)
+    {
       for (long long it = 0; it < my_tiles; ++it) {
         const long long tile = blockIdx.x + it * gridDim.x;
         const uint32_t ph = (uint32_t)(it & 1), ph2 = (uint32_t)((it >> 1) & 1);
@@ -642,7 +634,7 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
           // ---- value MLP with the attention aggregation fused in: this warp's 32 rows are the edges of destination 4*tile + eq
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            constexpr int cb = 64 * HALF;
+            const int cb = 64 * HALF;
             const int c0 = 16 * j;
             uint32_t v[16];
             tmem_ld16(tbase + (uint32_t)c0, v);
@@ -726,9 +718,7 @@ edge_mlp_v3_kernel(const float* __restrict__ P, const int* __restrict__ src, con
         if (lane == 0) mbar_arrive(bar(B_D_EMPTY0 + (int)ph));
         if (warp == 0) stamp(3, it, 2);
       }
-    };
-    if (warp < 4) epilogue(std::integral_constant<int, 0>{});
-    else epilogue(std::integral_constant<int, 1>{});
+    }
   }
   // ---- teardown
   tc_fence_before();

@@ -309,8 +309,15 @@ def main():
             except Exception:
                 tpeak, tsrc = 1400.0, 'fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)'
             ach = flops / t_m / 1e12
+            mlp_traffic = None          # DRAM bytes of one value-MLP (+ aggregation) launch from the committed ncu --set full capture
+            try:
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'edge_mlp_traffic.json')))
+                if tj.get('graphs') == G:
+                    mlp_traffic = tj['dram_bytes_per_launch']
+            except Exception:
+                pass
             extra['edge_mlp'] = {'kernel': 'edge_mlp_v3_kernel x4 per layer (engine mode %d)' % mode, 'bound': 'tensor', 'achieved': ach, 'peak': tpeak,
-                                 'unit': 'TFLOP/s', 'frac': ach / tpeak, 'traffic': None, 'peak_source': tsrc, 'executed_flops_per_layer': flops,
+                                 'unit': 'TFLOP/s', 'frac': ach / tpeak, 'traffic': mlp_traffic, 'peak_source': tsrc, 'executed_flops_per_layer': flops,
                                  'ms_per_layer': t_m * 1e3, 'share_of_step': ms_mlp / tot if tot else None,
                                  'note': 'bf16-split products count as executed flops (3 MMAs per fp32-class product); the kernel is bound by its '
                                          'CUDA-core LayerNorm/split stage, see DESIGN.md section 6'}

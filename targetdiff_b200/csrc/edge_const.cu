@@ -8,15 +8,44 @@
 
 #define EC_WARPS 8
 
-// One warp per destination node.  `src_prev` (optional) is the neighbour list of the previous forward on the same batch: a node
-// whose list is unchanged and that neither is a ligand atom nor has one among its neighbours keeps its edge types / gates
-// (protein atoms never move, reference models/uni_transformer.py:205-206, so those edges' lengths are step-invariant).
+// Phase 1, one warp per destination node.  `src_prev` (optional) is the neighbour list of the previous forward on the same batch: a
+// node whose list is unchanged and that neither is a ligand atom nor has one among its neighbours keeps its edge types / gates
+// (protein atoms never move, reference models/uni_transformer.py:205-206, so those edges' lengths are step-invariant).  All other
+// nodes go to `work_list`; their edges are evaluated by edge_gate_kernel (phase 2), one warp per edge, so that the heavy part is
+// load-balanced over the whole GPU instead of sitting in the few warps that happen to own ligand neighbourhoods.
 __global__ void __launch_bounds__(EC_WARPS * 32)
-edge_const_kernel(const float4* __restrict__ xm, const int* __restrict__ src, int* __restrict__ src_prev, int have_prev, int n_nodes, int k,
-                  const float* __restrict__ offsets, float coeff, const float* __restrict__ w1t, const float* __restrict__ b1,
-                  const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ w2, float b2,
-                  unsigned char* __restrict__ etype, float* __restrict__ e_w, int* __restrict__ slow_list, int* __restrict__ n_slow,
-                  unsigned char* __restrict__ rel_flag) {
+edge_touch_kernel(const float4* __restrict__ xm, const int* __restrict__ src, int* __restrict__ src_prev, int have_prev, int n_nodes, int k,
+                  unsigned char* __restrict__ rel_flag, int* __restrict__ work_list, int* __restrict__ n_work) {
+  const int lane = threadIdx.x & 31;
+  const int warp0 = blockIdx.x * EC_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * EC_WARPS;
+  for (int node = warp0; node < n_nodes; node += nwarps) {
+    const size_t e0 = (size_t)node * k;
+    const float4 xd = xm[node];
+    bool same = have_prev != 0, touch = xd.w != 0.0f;
+    for (int j = lane; j < k; j += 32) {
+      const int s = src[e0 + j];
+      if (src_prev) {
+        same = same && (src_prev[e0 + j] == s);
+        src_prev[e0 + j] = s;
+      }
+      if (s >= 0) touch = touch || (xm[s].w != 0.0f);
+      // "relevant" nodes = ligand atoms and their neighbours: the only rows the h2x sub-layers (and the last x2h) need
+      if (rel_flag && xd.w != 0.0f && s >= 0) rel_flag[s] = 1;
+    }
+    if (rel_flag && xd.w != 0.0f && lane == 0) rel_flag[node] = 1;
+    same = __all_sync(0xffffffffu, same);
+    touch = __any_sync(0xffffffffu, touch);
+    if (same && !touch) continue;
+    if (lane == 0) work_list[atomicAdd(n_work, 1)] = node;
+  }
+}
+
+// Phase 2, one warp per edge of the listed nodes: edge type and gate e_w = sigmoid(MLP(gaussians(|x_dst - x_src|))).
+__global__ void __launch_bounds__(EC_WARPS * 32)
+edge_gate_kernel(const float4* __restrict__ xm, const int* __restrict__ src, const int* __restrict__ work_list, const int* __restrict__ n_work,
+                 int k, const float* __restrict__ offsets, float coeff, const float* __restrict__ w1t, const float* __restrict__ b1,
+                 const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ w2, float b2,
+                 unsigned char* __restrict__ etype, float* __restrict__ e_w, int* __restrict__ slow_list, int* __restrict__ n_slow) {
   __shared__ float s_w1t[TD_NG * TD_H];
   __shared__ float s_b1[TD_H], s_g[TD_H], s_b[TD_H], s_w2[TD_H];
   for (int i = threadIdx.x; i < TD_NG * TD_H; i += blockDim.x) s_w1t[i] = w1t[i];
@@ -26,77 +55,57 @@ edge_const_kernel(const float4* __restrict__ xm, const int* __restrict__ src, in
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const float mu = offsets[lane < TD_NG ? lane : 0];
-  const int warp0 = blockIdx.x * EC_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * EC_WARPS;
-  for (int node = warp0; node < n_nodes; node += nwarps) {
-    const size_t e0 = (size_t)node * k;
-    const float4 xd = xm[node];
-    // ---- can this node be skipped?  (same neighbour list as last time, no ligand atom involved)
-    bool same = have_prev != 0, touch = xd.w != 0.0f;
-    for (int j = lane; j < k; j += 32) {
-      const int s = src[e0 + j];
-      if (src_prev) {
-        same = same && (src_prev[e0 + j] == s);
-        src_prev[e0 + j] = s;
-      }
-      if (s >= 0) touch = touch || (xm[s].w != 0.0f);
+  const long long warp0 = (long long)blockIdx.x * EC_WARPS + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * EC_WARPS;
+  const long long n_items = (long long)(*n_work) * k;
+  for (long long item = warp0; item < n_items; item += nwarps) {
+    const int node = work_list[item / k];
+    const size_t e = (size_t)node * k + (size_t)(item % k);
+    const int s = src[e];
+    if (s < 0) {
+      if (lane == 0) { etype[e] = 3; e_w[e] = 0.0f; }
+      continue;
     }
-    // "relevant" nodes = ligand atoms and their neighbours: the only rows the h2x sub-layers (and the last x2h) need
-    if (rel_flag && xd.w != 0.0f) {
-      if (lane == 0) rel_flag[node] = 1;
-      for (int j = lane; j < k; j += 32) {
-        const int s = src[e0 + j];
-        if (s >= 0) rel_flag[s] = 1;
-      }
+    const float4 xd = xm[node], xs = xm[s];
+    const float dx = xd.x - xs.x, dy = xd.y - xs.y, dz = xd.z - xs.z;
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float t = dist - mu;
+    const float gj = expf(coeff * (t * t));
+    float p[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) p[c] = s_b1[lane + 32 * c];
+#pragma unroll
+    for (int jj = 0; jj < TD_NG; ++jj) {
+      const float g = __shfl_sync(0xffffffffu, gj, jj);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) p[c] = fmaf(g, s_w1t[jj * TD_H + lane + 32 * c], p[c]);
     }
-    same = __all_sync(0xffffffffu, same);
-    touch = __any_sync(0xffffffffu, touch);
-    if (same && !touch) continue;
-    for (int j = 0; j < k; ++j) {
-      const size_t e = e0 + j;
-      const int s = src[e];
-      if (s < 0) {
-        if (lane == 0) { etype[e] = 3; e_w[e] = 0.0f; }
-        continue;
-      }
-      const float4 xs = xm[s];
-      const float dx = xd.x - xs.x, dy = xd.y - xs.y, dz = xd.z - xs.z;
-      const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
-      const float t = dist - mu;
-      const float gj = expf(coeff * (t * t));
-      float p[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) p[c] = s_b1[lane + 32 * c];
-#pragma unroll
-      for (int jj = 0; jj < TD_NG; ++jj) {
-        const float g = __shfl_sync(0xffffffffu, gj, jj);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) p[c] = fmaf(g, s_w1t[jj * TD_H + lane + 32 * c], p[c]);
-      }
-      ln_relu_128(p, s_g, s_b, lane);
-      float acc = (p[0] * s_w2[lane] + p[1] * s_w2[lane + 32]) + (p[2] * s_w2[lane + 64] + p[3] * s_w2[lane + 96]);
-      acc = warp_sum(acc) + b2;
-      if (lane == 0) {
-        const bool ns = xs.w != 0.0f, nd = xd.w != 0.0f;
-        const int ty = ns ? (nd ? 0 : 1) : (nd ? 2 : 3);
-        etype[e] = (unsigned char)ty;
-        e_w[e] = 1.0f / (1.0f + expf(-acc));
-        // every edge that touches a ligand atom (type != 3): compact list for edge_slow_kernel (order is irrelevant)
-        if (ty != 3 && slow_list) slow_list[atomicAdd(n_slow, 1)] = (int)e;
-      }
+    ln_relu_128(p, s_g, s_b, lane);
+    float acc = (p[0] * s_w2[lane] + p[1] * s_w2[lane + 32]) + (p[2] * s_w2[lane + 64] + p[3] * s_w2[lane + 96]);
+    acc = warp_sum(acc) + b2;
+    if (lane == 0) {
+      const bool ns = xs.w != 0.0f, nd = xd.w != 0.0f;
+      const int ty = ns ? (nd ? 0 : 1) : (nd ? 2 : 3);
+      etype[e] = (unsigned char)ty;
+      e_w[e] = 1.0f / (1.0f + expf(-acc));
+      // every edge that touches a ligand atom (type != 3): compact list for edge_slow_kernel (order is irrelevant)
+      if (ty != 3 && slow_list) slow_list[atomicAdd(n_slow, 1)] = (int)e;
     }
   }
 }
 
 void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int have_prev, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
-                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, unsigned char* rel_flag, cudaStream_t st) {
+                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, unsigned char* rel_flag, int* work_list, int* n_work,
+                          cudaStream_t st) {
   if (n_nodes == 0) return;
   int blocks = (n_nodes + EC_WARPS - 1) / EC_WARPS;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (n_slow) cudaMemsetAsync(n_slow, 0, sizeof(int), st);
   if (rel_flag) cudaMemsetAsync(rel_flag, 0, (size_t)n_nodes, st);
-  edge_const_kernel<<<blocks, EC_WARPS * 32, 0, st>>>(xm, src, src_prev, have_prev, n_nodes, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2, etype,
-                                                      e_w, slow_list, n_slow, rel_flag);
+  cudaMemsetAsync(n_work, 0, sizeof(int), st);
+  edge_touch_kernel<<<blocks, EC_WARPS * 32, 0, st>>>(xm, src, src_prev, have_prev, n_nodes, k, rel_flag, work_list, n_work);
+  edge_gate_kernel<<<148 * 8, EC_WARPS * 32, 0, st>>>(xm, src, work_list, n_work, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2, etype, e_w,
+                                                     slow_list, n_slow);
 }
 
 // Per-layer edge length |x_dst - x_src| (reference models/uni_transformer.py:188-189) for every slot, from the layer's input

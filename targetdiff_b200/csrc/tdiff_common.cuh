@@ -113,7 +113,8 @@ __device__ __forceinline__ void tile_gemm_128(const float* __restrict__ As, cons
 void td_launch_knn(const float4* xm, const int* node_ptr, int n_graphs, int max_nodes_per_graph, int k, int* src, cudaStream_t st);
 void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int have_prev, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
-                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, unsigned char* rel_flag, cudaStream_t st);
+                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, unsigned char* rel_flag, int* work_list, int* n_work,
+                          cudaStream_t st);
 void td_launch_protein_embed(const float* feat, int n_protein, int fdim, const float* w, const float* b, const int* prot_node,
                              float* h0, cudaStream_t st);
 void td_launch_init_h(const float* h0, const float4* xm, const int* lig_v, const int* node_lig, const float* wl_t, const float* bl,

@@ -26,6 +26,9 @@ CASES = {
                         tape_seed=7, num_steps=5),
     'chain_full_T20': dict(cfg={'num_diffusion_timesteps': 20}, weight_seed=4,
                            batch=dict(seed=5, n_graphs=1, n_protein=50, ligand_sizes=[10]), tape_seed=9, num_steps=None),
+    # likelihood_estimation at mixed time steps (incl. the decoder branch t = 0) and the prior branch (t = T)
+    'likelihood': dict(cfg={}, weight_seed=5, batch=dict(seed=4, n_graphs=3, n_protein=64, ligand_sizes=[7, 10, 4]), tape_seed=9,
+                       time_steps=[0, 999, 417]),
 }
 
 
@@ -47,7 +50,15 @@ def run_case(name):
     b = synth.make_batch(**case['batch'])
     out = {}
     with torch.no_grad():
-        if 'num_steps' not in case:
+        if 'time_steps' in case:
+            pn, vu = synth.make_tape(case['tape_seed'], 1, len(b['batch_ligand']))
+            args = (b['protein_pos'], b['protein_v'], b['batch_protein'], b['init_ligand_pos'], b['init_ligand_v'], b['batch_ligand'])
+            with refload.noise_tape(pn, vu):
+                kp, kv = model.likelihood_estimation(*args, time_step=torch.tensor(case['time_steps']))
+            T = sd['betas'].shape[0]
+            kp_T, kv_T = model.likelihood_estimation(*args, time_step=torch.full((len(case['time_steps']),), T))
+            out = dict(kl_pos=kp, kl_v=kv, kl_pos_prior=kp_T, kl_v_prior=kv_T)
+        elif 'num_steps' not in case:
             pp, lp, _ = ref.center_pos(b['protein_pos'], b['init_ligand_pos'], b['batch_protein'], b['batch_ligand'])
             # capture the backbone's intermediate state through its own return_all / a forward hook
             grabbed = {}
@@ -81,8 +92,9 @@ def run_case(name):
 
 
 def main():
+    import sys
     os.makedirs(GOLDEN, exist_ok=True)
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):
         arrs = run_case(name)
         path = os.path.join(GOLDEN, name + '.npz')
         np.savez_compressed(path, **arrs)

@@ -56,8 +56,16 @@ def noise_tape(pos_noise, v_uniform):
         state['u'] += 1
         return out.clone()
 
-    torch.randn_like, torch.rand_like = randn_like, rand_like
+    orig_normal_ = torch.Tensor.normal_
+
+    def normal_(t, *a, **k):            # `pos_noise.normal_()` of likelihood_estimation (:581-582) reads the position tape too
+        out = pos_noise[state['p']].to(t)
+        assert out.shape == t.shape
+        state['p'] += 1
+        return t.copy_(out)
+
+    torch.randn_like, torch.rand_like, torch.Tensor.normal_ = randn_like, rand_like, normal_
     try:
         yield state
     finally:
-        torch.randn_like, torch.rand_like = orig_randn_like, orig_rand_like
+        torch.randn_like, torch.rand_like, torch.Tensor.normal_ = orig_randn_like, orig_rand_like, orig_normal_

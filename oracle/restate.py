@@ -358,3 +358,66 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
             step_callback(s, i, preds, ligand_pos, ligand_v)
     return {'pos': ligand_pos + offset[batch_ligand], 'v': ligand_v, 'pos_traj': pos_traj, 'v_traj': v_traj,
             'v0_traj': v0_traj, 'vt_traj': vt_traj}
+
+
+# ----------------------------------------------------------------------------------------------
+# n3  likelihood estimation (second consumer of `forward`)     models/molopt_score_model.py:133-155,411-438,470-489,565-617
+# ----------------------------------------------------------------------------------------------
+def _normal_kl(mean1, logvar1, mean2, logvar2):
+    d = mean1 - mean2                                                                    # :143-148
+    return (0.5 * (-1.0 + logvar2 - logvar1 + torch.exp(logvar1 - logvar2) + d ** 2 * torch.exp(-logvar2))).sum(-1)
+
+
+def _scatter_mean_rows(v, batch, B):
+    s = torch.zeros(B, dtype=v.dtype).index_add_(0, batch, v)
+    c = torch.zeros(B, dtype=v.dtype).index_add_(0, batch, torch.ones_like(v))
+    c[c < 1] = 1
+    return s / c
+
+
+def likelihood_estimation(sd, cfg, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v, batch_ligand, time_step,
+                          pos_noise=None, v_uniform=None):
+    """ScorePosNet3D.likelihood_estimation (:565-617): per-graph (kl_pos, kl_v) at `time_step` [B] (< T), or the two prior KL
+    terms when time_step == T everywhere.  RNG replaced by `pos_noise` [Nl,3] (the in-place normal_ of :581-582) and
+    `v_uniform` [Nl,K] (rand_like inside q_v_sample, :394-398 via :160-166)."""
+    c = dict(DEFAULT_MODEL_CONFIG, **(cfg or {}))
+    T = c['num_diffusion_timesteps']
+    K = sd['ligand_atom_emb.weight'].shape[1]
+    B = int(batch_protein.max()) + 1
+    protein_pos, ligand_pos, _ = center_pos(protein_pos, ligand_pos, batch_protein, batch_ligand, 'protein')
+    if bool((time_step == T).all()):
+        last = torch.full((B,), T - 1, dtype=torch.long)
+        a_pos = extract(sd['alphas_cumprod'], last, batch_ligand)                        # :430-438
+        mean = a_pos.sqrt() * ligand_pos
+        logvar = torch.log((1.0 - a_pos).sqrt())
+        kl_pos = _scatter_mean_rows(_normal_kl(torch.zeros_like(mean), torch.zeros_like(logvar), mean, logvar), batch_ligand, B)
+        # :573 passes batch_ligand (graph ids) where atom types are expected -- restated as written
+        log_v0 = index_to_log_onehot(batch_ligand, K)
+        log_qT = q_v_pred(sd, log_v0, last, batch_ligand, K)                             # :411-417
+        log_half = -torch.log(K * torch.ones_like(log_qT))
+        kl_v = _scatter_mean_rows((log_qT.exp() * (log_qT - log_half)).sum(1), batch_ligand, B)
+        return kl_pos, kl_v
+    assert bool((time_step < T).all())
+    a_pos = sd['alphas_cumprod'].index_select(0, time_step)[batch_ligand].unsqueeze(-1)  # :578-579
+    xt = a_pos.sqrt() * ligand_pos + (1.0 - a_pos).sqrt() * pos_noise                    # :583
+    log_v0 = index_to_log_onehot(ligand_v, K)
+    vt = log_sample_categorical_from_uniform(q_v_pred(sd, log_v0, time_step, batch_ligand, K), v_uniform)   # :586
+    log_vt = index_to_log_onehot(vt, K)
+    out = forward(sd, cfg, protein_pos, protein_v, batch_protein, xt, vt, batch_ligand)  # :588-597
+    mean_model = q_pos_posterior(sd, out['pred_ligand_pos'], xt, time_step, batch_ligand)   # :600-603
+    log_recon = F.log_softmax(out['pred_ligand_v'], dim=-1)
+    log_model = q_v_posterior(sd, log_recon, log_vt, time_step, batch_ligand, K)
+    log_true = q_v_posterior(sd, log_v0, log_vt, time_step, batch_ligand, K)
+    mask = (time_step == 0).float()[batch_ligand]
+    # position term (:470-482)
+    logvar = extract(sd['posterior_logvar'], time_step, batch_ligand)
+    mean_true = q_pos_posterior(sd, ligand_pos, xt, time_step, batch_ligand)
+    kl_p = _normal_kl(mean_true, logvar, mean_model, logvar) / np.log(2.)
+    ls = 0.5 * logvar
+    nll_p = -((-((ligand_pos - mean_model) ** 2) / (2 * torch.exp(ls * 2)) - ls - np.log(np.sqrt(2 * np.pi))).sum(-1))
+    kl_pos = _scatter_mean_rows(mask * nll_p + (1. - mask) * kl_p, batch_ligand, B)
+    # type term (:484-489)
+    kl_c = (log_true.exp() * (log_true - log_model)).sum(1)
+    nll_c = -(log_v0.exp() * log_model).sum(1)
+    kl_v = _scatter_mean_rows(mask * nll_c + (1. - mask) * kl_c, batch_ligand, B)
+    return kl_pos, kl_v

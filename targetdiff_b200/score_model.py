@@ -9,9 +9,11 @@ The modules below only *hold parameters*: every computation goes through libtdif
 include/tdiff.h).  There is no PyTorch/CPU execution path; calling forward on CPU tensors raises.
 """
 import ctypes
+import math
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 import torch.nn as nn
 
 from . import _lib
@@ -353,8 +355,84 @@ class ScorePosNet3D(nn.Module):
     def get_diffusion_loss(self, *a, **k):
         raise NotImplementedError('training is out of scope of the B200 sampling engine (SURVEY.md section 2)')
 
-    def likelihood_estimation(self, *a, **k):
-        raise NotImplementedError('likelihood_estimation is a "next" row (SURVEY.md 8(f) n3)')
+    # ------------------------------------------------------------------ second consumer of forward
+    def _tab(self, name, t, batch):
+        return getattr(self, name)[t][batch].unsqueeze(-1)
+
+    def _q_v_pred(self, log_v0, t, batch, one_step=False):
+        """log q(v_t | v_0) (or the single-step kernel), reference models/molopt_score_model.py:371-392"""
+        la = self._tab('log_alphas_v' if one_step else 'log_alphas_cumprod_v', t, batch)
+        l1 = self._tab('log_one_minus_alphas_v' if one_step else 'log_one_minus_alphas_cumprod_v', t, batch)
+        x, y = log_v0 + la, l1 - math.log(self.num_classes)
+        m = torch.max(x, y)
+        return m + torch.log(torch.exp(x - m) + torch.exp(y - m))
+
+    def _q_v_posterior(self, log_v0, log_vt, t, batch):
+        un = self._q_v_pred(log_v0, (t - 1).clamp(min=0), batch) + self._q_v_pred(log_vt, t, batch, one_step=True)   # :401-409
+        return un - torch.logsumexp(un, dim=-1, keepdim=True)
+
+    def _log_onehot(self, idx):
+        if int(idx.max()) >= self.num_classes:
+            raise ValueError('atom-type index %d >= num_classes %d' % (int(idx.max()), self.num_classes))   # reference assert, :125
+        return torch.log(F.one_hot(idx, self.num_classes).float().clamp(min=1e-30))
+
+    @torch.no_grad()
+    def likelihood_estimation(self, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v, batch_ligand, time_step, noise=None):
+        """Per-graph variational-bound terms (kl_pos, kl_v) at `time_step` [B], or the prior KL pair when `time_step == T`
+        everywhere (reference models/molopt_score_model.py:565-617; caller scripts/likelihood_est_diffusion.py:30-40).
+        The network evaluation is `forward` on libtdiff.so; the few [Nl,13]-sized formulas around it are torch elementwise ops
+        on the caller's device.  `noise=(pos_noise [Nl,3], v_uniform [Nl,K])` replaces the two RNG draws (parity tests)."""
+        from . import ops
+        T, K = self.num_timesteps, self.num_classes
+        dev = protein_pos.device
+        time_step = time_step.to(dev, torch.long)
+        B = int(batch_protein.max()) + 1
+        if time_step.numel() != B:
+            raise ValueError('time_step must have one entry per graph')
+        offset = ops.scatter_mean3(protein_pos.float(), batch_protein)                      # center_pos(mode='protein'), :110-120
+        protein_pos = protein_pos.float() - offset[batch_protein]
+        x0 = ligand_pos.float() - offset[batch_ligand]
+        cnt = torch.bincount(batch_ligand, minlength=B).clamp(min=1).float()
+        graph_mean = lambda v: torch.zeros(B, device=dev).index_add_(0, batch_ligand, v) / cnt
+        normal_kl = lambda m1, lv1, m2, lv2: (0.5 * (-1.0 + lv2 - lv1 + torch.exp(lv1 - lv2) + (m1 - m2) ** 2 * torch.exp(-lv2))).sum(-1)
+        is_prior = bool((time_step == T).all())
+        if not is_prior and not bool((time_step < T).all()):
+            raise ValueError('time_step must be all == num_timesteps or all < num_timesteps')        # reference assert, :570
+        if is_prior:
+            last = torch.full((B,), T - 1, dtype=torch.long, device=dev)
+            a_pos = self._tab('alphas_cumprod', last, batch_ligand)
+            mean, logvar = a_pos.sqrt() * x0, torch.log((1.0 - a_pos).sqrt())
+            kl_pos = graph_mean(normal_kl(torch.zeros_like(mean), torch.zeros_like(logvar), mean, logvar))
+            log_qT = self._q_v_pred(self._log_onehot(batch_ligand), last, batch_ligand)          # graph ids as types, as the reference (:573)
+            kl_v = graph_mean((log_qT.exp() * (log_qT + math.log(K))).sum(1))
+            return kl_pos, kl_v
+        if noise is None:
+            pos_noise = torch.randn_like(x0)
+            v_uniform = torch.rand(x0.shape[0], K, device=dev)
+        else:
+            pos_noise, v_uniform = noise[0].to(dev, torch.float32), noise[1].to(dev, torch.float32)
+        a_pos = self.alphas_cumprod.index_select(0, time_step)[batch_ligand].unsqueeze(-1)
+        xt = a_pos.sqrt() * x0 + (1.0 - a_pos).sqrt() * pos_noise                                     # :583
+        log_v0 = self._log_onehot(ligand_v)
+        gumbel = -torch.log(-torch.log(v_uniform + 1e-30) + 1e-30)
+        vt = (gumbel + self._q_v_pred(log_v0, time_step, batch_ligand)).argmax(dim=-1)                # q_v_sample, :394-398
+        log_vt = self._log_onehot(vt)
+        out = self.forward(protein_pos, protein_v, batch_protein, xt, vt, batch_ligand, time_step=time_step)
+        c0 = self._tab('posterior_mean_c0_coef', time_step, batch_ligand)
+        ct = self._tab('posterior_mean_ct_coef', time_step, batch_ligand)
+        mean_model, mean_true = c0 * out['pred_ligand_pos'] + ct * xt, c0 * x0 + ct * xt              # q_pos_posterior, :424-428
+        log_model = self._q_v_posterior(F.log_softmax(out['pred_ligand_v'], dim=-1), log_vt, time_step, batch_ligand)
+        log_true = self._q_v_posterior(log_v0, log_vt, time_step, batch_ligand)
+        decoder = (time_step == 0).float()[batch_ligand]
+        logvar = self._tab('posterior_logvar', time_step, batch_ligand)
+        kl_p = normal_kl(mean_true, logvar, mean_model, logvar) / math.log(2.)                        # compute_pos_Lt, :470-482
+        ls = 0.5 * logvar
+        nll_p = ((x0 - mean_model) ** 2 / (2 * torch.exp(2 * ls)) + ls + math.log(math.sqrt(2 * math.pi))).sum(-1)
+        kl_pos = graph_mean(decoder * nll_p + (1. - decoder) * kl_p)
+        kl_c = (log_true.exp() * (log_true - log_model)).sum(1)                                       # compute_v_Lt, :484-489
+        nll_c = -(log_v0.exp() * log_model).sum(1)
+        kl_v = graph_mean(decoder * nll_c + (1. - decoder) * kl_c)
+        return kl_pos, kl_v
 
     @torch.no_grad()
     def fetch_embedding(self, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v, batch_ligand):

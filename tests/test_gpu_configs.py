@@ -190,3 +190,28 @@ def test_relevant_node_restriction_is_exact(monkeypatch):
     assert torch.equal(res[0]['pos'], res[1]['pos']) and torch.equal(res[0]['v'], res[1]['v'])
     assert torch.equal(torch.stack(res[0]['v0_traj']), torch.stack(res[1]['v0_traj']))
     assert torch.equal(torch.stack(res[0]['pos_traj']), torch.stack(res[1]['pos_traj']))
+
+
+def test_likelihood_estimation_vs_oracle_and_golden():
+    """SURVEY 8(f) n3 (reference models/molopt_score_model.py:565-617): the network call runs on libtdiff.so; compared with the CPU
+    oracle on the same noise and with the vectors the reference itself wrote (tests/golden/likelihood.npz)."""
+    import os
+    import numpy as np
+    from oracle.make_golden import CASES, GOLDEN
+    case = CASES['likelihood']
+    model, sd = _model(case['weight_seed'])
+    b = synth.make_batch(**case['batch'])
+    pn, vu = synth.make_tape(case['tape_seed'], 1, len(b['batch_ligand']))
+    t = torch.tensor(case['time_steps'])
+    want = restate.likelihood_estimation(sd, None, *_args(b, 'cpu'), t, pn[0], vu[0])
+    got = model.likelihood_estimation(*_args(b), time_step=t.to(DEV), noise=(pn[0], vu[0]))
+    g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLDEN, 'likelihood.npz')).items()}
+    for w, x, name in zip(want, got, ('kl_pos', 'kl_v')):
+        torch.testing.assert_close(x.cpu(), w, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(x.cpu(), g[name], rtol=1e-4, atol=1e-5)
+    got = model.likelihood_estimation(*_args(b), time_step=torch.full((3,), model.num_timesteps, device=DEV))
+    torch.testing.assert_close(got[0].cpu(), g['kl_pos_prior'], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(got[1].cpu(), g['kl_v_prior'], rtol=1e-5, atol=1e-6)
+    # unseeded call: finite, one value per graph
+    kp, kv = model.likelihood_estimation(*_args(b), time_step=t.to(DEV))
+    assert kp.shape == kv.shape == (3,) and torch.isfinite(kp).all() and torch.isfinite(kv).all()

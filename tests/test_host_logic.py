@@ -86,3 +86,35 @@ def test_sample_diffusion_ligand_bookkeeping():
     seed_all(2)
     out2 = sample_diffusion_ligand(m, data, num_samples=3, batch_size=16, device='cpu', num_steps=2, sample_num_atoms='prior')
     assert len(out2[0]) == 3 and all(len(p) >= 1 for p in out2[0])
+
+
+def test_likelihood_estimation_host_math_against_oracle(monkeypatch):
+    """The [Nl,13]-sized formulas around the network call (reference models/molopt_score_model.py:565-617).  The network itself
+    is replaced by the oracle's CPU forward here (test infrastructure only -- the product path has no CPU execution); the GPU
+    test `test_likelihood_estimation_vs_oracle` runs the real thing."""
+    from oracle import restate, synth
+    from targetdiff_b200 import ops
+    from targetdiff_b200.score_model import ScorePosNet3D
+    sd = synth.make_state_dict(5, schedules=restate.make_schedules())
+    model = ScorePosNet3D(default_model_config(), synth.PROTEIN_FEATURE_DIM, synth.LIGAND_NUM_CLASSES)
+    model.load_state_dict(sd, strict=True)
+    b = synth.make_batch(4, 3, n_protein=40, ligand_sizes=[7, 10, 4])
+    args = (b['protein_pos'], b['protein_v'], b['batch_protein'], b['init_ligand_pos'], b['init_ligand_v'], b['batch_ligand'])
+    pn, vu = synth.make_tape(9, 1, len(b['batch_ligand']))
+
+    def cpu_mean3(src, batch):
+        n = int(batch.max()) + 1
+        return torch.zeros(n, 3).index_add_(0, batch, src) / torch.bincount(batch, minlength=n).clamp(min=1)[:, None]
+
+    def oracle_forward(pp, pv, bp, lp, lv, bl, time_step=None, **k):
+        return restate.forward(sd, None, pp, pv, bp, lp, lv, bl)
+
+    monkeypatch.setattr(ops, 'scatter_mean3', cpu_mean3)
+    monkeypatch.setattr(model, 'forward', oracle_forward)
+    for t in (torch.tensor([0, 999, 417]), torch.full((3,), 1000)):
+        want = restate.likelihood_estimation(sd, None, *args, t, pn[0], vu[0])
+        got = model.likelihood_estimation(*args, time_step=t, noise=(pn[0], vu[0]))
+        for w, g in zip(want, got):
+            torch.testing.assert_close(g, w, rtol=2e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        model.likelihood_estimation(*args, time_step=torch.tensor([0, 1000, 5]), noise=(pn[0], vu[0]))

@@ -53,3 +53,24 @@ def test_chain_golden(name):
     assert torch.equal(torch.stack(r['v_traj']), g['v_traj'])
     _close(torch.stack(r['v0_traj']), g['v0_traj'], 'v0_traj')
     _close(torch.stack(r['vt_traj']), g['vt_traj'], 'vt_traj')
+
+
+def _likelihood_inputs():
+    case = CASES['likelihood']
+    sd = synth.make_state_dict(case['weight_seed'], schedules=restate.make_schedules())
+    b = synth.make_batch(**case['batch'])
+    pn, vu = synth.make_tape(case['tape_seed'], 1, len(b['batch_ligand']))
+    args = (b['protein_pos'], b['protein_v'], b['batch_protein'], b['init_ligand_pos'], b['init_ligand_v'], b['batch_ligand'])
+    return case, sd, args, pn[0], vu[0]
+
+
+def test_likelihood_golden():
+    """oracle restatement of likelihood_estimation vs vectors written by the reference itself."""
+    case, sd, args, pn, vu = _likelihood_inputs()
+    g = _load('likelihood')
+    kp, kv = restate.likelihood_estimation(sd, None, *args, torch.tensor(case['time_steps']), pn, vu)
+    _close(kp, g['kl_pos'], 'kl_pos')
+    _close(kv, g['kl_v'], 'kl_v')
+    kp, kv = restate.likelihood_estimation(sd, None, *args, torch.full((3,), 1000))
+    _close(kp, g['kl_pos_prior'], 'kl_pos_prior')
+    _close(kv, g['kl_v_prior'], 'kl_v_prior')

@@ -87,3 +87,23 @@ def test_sampling_chain_bit_exact(ref_model):
     assert torch.equal(want['pos'], got['pos']) and torch.equal(want['v'], got['v'])
     for k in ('pos_traj', 'v_traj', 'v0_traj', 'vt_traj'):
         assert all(torch.equal(a, c) for a, c in zip(want[k], got[k])), k
+
+
+@pytest.mark.parametrize('steps', [[0, 999], [417, 3], None])
+def test_likelihood_estimation_matches_reference(ref_model, steps):
+    """the second consumer of `forward` (reference models/molopt_score_model.py:565-617), incl. the decoder
+    branch (t = 0) and the prior branch (time_step == T)."""
+    _, model = ref_model
+    sd = synth.make_state_dict(5, schedules=restate.make_schedules())
+    model.load_state_dict(sd, strict=True)
+    b = synth.make_batch(4, 2, n_protein=52, ligand_sizes=[7, 10])
+    Nl = len(b['batch_ligand'])
+    pn, vu = synth.make_tape(9, 1, Nl)
+    t = torch.tensor(steps) if steps is not None else torch.full((2,), 1000)
+    args = (b['protein_pos'], b['protein_v'], b['batch_protein'], b['init_ligand_pos'], b['init_ligand_v'], b['batch_ligand'])
+    with torch.no_grad(), refload.noise_tape(pn, vu):
+        want = model.likelihood_estimation(*args, time_step=t)
+    got = restate.likelihood_estimation(sd, None, *args, t, pn[0], vu[0])
+    for w, g in zip(want, got):
+        assert w.shape == g.shape == (2,)
+        torch.testing.assert_close(g, w, rtol=1e-6, atol=1e-7)

@@ -51,7 +51,9 @@ typedef struct tdiff_config {
   int32_t num_classes;       /* ligand_atom_feature_dim, 13 */
   int32_t protein_feat_dim;  /* protein_atom_feature_dim, 27 */
   int32_t num_timesteps;     /* num_diffusion_timesteps, 1000 */
-  int32_t reserved[8];       /* must be 0 */
+  int32_t model_mean_type;   /* 0 = 'C0' (network predicts x0), 1 = 'noise' (x0 from the predicted displacement,
+                              * reference models/molopt_score_model.py:419-422,663-666) */
+  int32_t reserved[7];       /* must be 0 */
 } tdiff_config;
 
 /* One state_dict entry (reference key name, fp32, host memory).  SURVEY.md Appendix D lists the 384 keys. */

@@ -326,10 +326,10 @@ def forward(sd, cfg, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v
 # ----------------------------------------------------------------------------------------------
 def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand_pos, init_ligand_v, batch_ligand,
                      pos_noise, v_uniform, num_steps=None, center_pos_mode='protein', step_callback=None):
-    """C0-mode sampler driven by a noise tape: pos_noise [S,Nl,3], v_uniform [S,Nl,K].
+    """Sampler (model_mean_type C0 or noise) driven by a noise tape: pos_noise [S,Nl,3], v_uniform [S,Nl,K].
     Returns the reference's dict ('pos','v','pos_traj','v_traj','v0_traj','vt_traj'), trajectories as lists."""
     cfg = dict(DEFAULT_MODEL_CONFIG, **(cfg or {}))
-    assert cfg['model_mean_type'] == 'C0'
+    assert cfg['model_mean_type'] in ('C0', 'noise')
     T = sd['betas'].shape[0]
     K = sd['ligand_atom_emb.weight'].shape[1]
     if num_steps is None:
@@ -343,6 +343,10 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
         t = torch.full((num_graphs,), i, dtype=torch.long)                               # :651
         preds = forward(sd, cfg, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v, batch_ligand)
         pos0, v0 = preds['pred_ligand_pos'], preds['pred_ligand_v']                      # :667-669
+        if cfg['model_mean_type'] == 'noise':                                            # :663-666 with :419-422
+            eps = pos0 - ligand_pos
+            pos0 = extract(sd['sqrt_recip_alphas_cumprod'], t, batch_ligand) * ligand_pos - \
+                extract(sd['sqrt_recipm1_alphas_cumprod'], t, batch_ligand) * eps
         pos_mean = q_pos_posterior(sd, pos0, ligand_pos, t, batch_ligand)                # :673
         logvar = extract(sd['posterior_logvar'], t, batch_ligand)                        # :674
         nonzero = (1 - (t == 0).float())[batch_ligand].unsqueeze(-1)                     # :676

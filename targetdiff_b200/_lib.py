@@ -20,7 +20,7 @@ class TdiffError(RuntimeError):
 class tdiff_config(ctypes.Structure):
     _fields_ = [('hidden_dim', ctypes.c_int32), ('n_heads', ctypes.c_int32), ('num_layers', ctypes.c_int32), ('knn', ctypes.c_int32),
                 ('num_r_gaussian', ctypes.c_int32), ('num_classes', ctypes.c_int32), ('protein_feat_dim', ctypes.c_int32),
-                ('num_timesteps', ctypes.c_int32), ('reserved', ctypes.c_int32 * 8)]
+                ('num_timesteps', ctypes.c_int32), ('model_mean_type', ctypes.c_int32), ('reserved', ctypes.c_int32 * 7)]
 
 
 class tdiff_tensor(ctypes.Structure):

@@ -47,7 +47,7 @@ def default_sampling_config():
 
 
 # Values the sm_100a engine implements; anything else is rejected loudly (SURVEY.md 8(b) "should-reject-clearly").
-_SUPPORTED = dict(model_mean_type=('C0',), beta_schedule=('sigmoid', 'linear', 'quad', 'const', 'jsd', 'cosine'),
+_SUPPORTED = dict(model_mean_type=('C0', 'noise'), beta_schedule=('sigmoid', 'linear', 'quad', 'const', 'jsd', 'cosine'),
                   v_beta_schedule=('cosine',), time_emb_dim=(0,), node_indicator=(True,), model_type=('uni_o2',),
                   num_blocks=(1,), hidden_dim=(128,), n_heads=(16,), edge_feat_dim=(4,), num_r_gaussian=(20,), act_fn=('relu',),
                   norm=(True,), cutoff_mode=('knn',), ew_net_type=('global',), num_x2h=(1,), num_h2x=(1,), x2h_out_fc=(False,),

@@ -70,7 +70,8 @@ struct tdiff_engine {
   const float *ew_w1t = nullptr, *ew_b1 = nullptr, *ew_g = nullptr, *ew_b = nullptr, *ew_w2 = nullptr, *ew_off = nullptr;
   float ew_b2 = 0.f, ew_coeff = -0.5f;
   const float *hd_w1t = nullptr, *hd_b1 = nullptr, *hd_w2 = nullptr, *hd_b2 = nullptr;
-  const float *t_c0 = nullptr, *t_ct = nullptr, *t_logvar = nullptr, *t_la = nullptr, *t_l1ma = nullptr, *t_lca = nullptr, *t_l1mca = nullptr;
+  const float *t_c0 = nullptr, *t_ct = nullptr, *t_logvar = nullptr, *t_la = nullptr, *t_l1ma = nullptr, *t_lca = nullptr, *t_l1mca = nullptr,
+              *t_sra = nullptr, *t_srm1 = nullptr;
   // ---- batch
   bool bound = false, has_ligand = false, have_graph = false;
   bool restrict_last = false;           // sampling loop only: the last layer's x2h is evaluated for the relevant nodes only
@@ -264,6 +265,10 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     return set_err(TDIFF_EINVAL, "unsupported model shape: hidden_dim=%d n_heads=%d num_r_gaussian=%d (kernels are built for 128/16/20)",
                    cfg->hidden_dim, cfg->n_heads, cfg->num_r_gaussian);
   if (cfg->knn < 1 || cfg->knn > TD_KMAX) return set_err(TDIFF_EINVAL, "knn=%d outside 1..%d", cfg->knn, TD_KMAX);
+  if (cfg->model_mean_type != 0 && cfg->model_mean_type != 1)
+    return set_err(TDIFF_EINVAL, "model_mean_type=%d (0 = C0, 1 = noise)", cfg->model_mean_type);
+  for (int r : cfg->reserved)
+    if (r != 0) return set_err(TDIFF_EINVAL, "tdiff_config.reserved must be 0");
   if (cfg->num_layers < 1 || cfg->num_classes < 1 || cfg->num_classes > TD_CMAX || cfg->protein_feat_dim < 1 || cfg->num_timesteps < 1)
     return set_err(TDIFF_EINVAL, "bad config (num_layers=%d num_classes=%d protein_feat_dim=%d num_timesteps=%d)", cfg->num_layers,
                    cfg->num_classes, cfg->protein_feat_dim, cfg->num_timesteps);
@@ -285,8 +290,9 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
   for (int i = 0; i < n_entries; ++i)
     if (sd[i].name) pk.byname[sd[i].name] = &sd[i];
   const int T = cfg->num_timesteps, KC = cfg->num_classes, F = cfg->protein_feat_dim, L = cfg->num_layers;
-  struct { const char* name; size_t off; } tabs[7] = {{"posterior_mean_c0_coef", 0}, {"posterior_mean_ct_coef", 0}, {"posterior_logvar", 0},
-      {"log_alphas_v", 0}, {"log_one_minus_alphas_v", 0}, {"log_alphas_cumprod_v", 0}, {"log_one_minus_alphas_cumprod_v", 0}};
+  struct { const char* name; size_t off; } tabs[9] = {{"posterior_mean_c0_coef", 0}, {"posterior_mean_ct_coef", 0}, {"posterior_logvar", 0},
+      {"log_alphas_v", 0}, {"log_one_minus_alphas_v", 0}, {"log_alphas_cumprod_v", 0}, {"log_one_minus_alphas_cumprod_v", 0},
+      {"sqrt_recip_alphas_cumprod", 0}, {"sqrt_recipm1_alphas_cumprod", 0}};
   for (auto& t : tabs) {
     const float* p = pk.get(t.name, T);
     t.off = pk.alloc(T);
@@ -378,6 +384,7 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
   const unsigned char* IM = e->img_arena;
   e->t_c0 = A + tabs[0].off; e->t_ct = A + tabs[1].off; e->t_logvar = A + tabs[2].off; e->t_la = A + tabs[3].off;
   e->t_l1ma = A + tabs[4].off; e->t_lca = A + tabs[5].off; e->t_l1mca = A + tabs[6].off;
+  e->t_sra = A + tabs[7].off; e->t_srm1 = A + tabs[8].off;
   e->w_prot = A + o_wp; e->b_prot = A + o_bp; e->wl_t = A + o_wl; e->bl = A + o_bl;
   e->ew_w1t = A + o_gw1; e->ew_b1 = A + o_gb1; e->ew_g = A + o_gg; e->ew_b = A + o_gb; e->ew_w2 = A + o_gw2; e->ew_off = A + o_goff;
   e->hd_w1t = A + o_hw1; e->hd_b1 = A + o_hb1; e->hd_w2 = A + o_hw2; e->hd_b2 = A + o_hb2;
@@ -734,6 +741,7 @@ extern "C" int tdiff_sample(tdiff_engine* e, int num_steps, const float* d_pos_n
   A.step = e->step.as<int>(); A.lig_node = e->lig_node.as<int>(); A.lig_graph = e->lig_graph.as<int>();
   A.logits = e->logits.as<float>(); A.offset = e->offset.as<float4>();
   A.c0 = e->t_c0; A.ct = e->t_ct; A.logvar = e->t_logvar; A.la_v = e->t_la; A.l1ma_v = e->t_l1ma; A.lca_v = e->t_lca; A.l1mca_v = e->t_l1mca;
+  A.sra = e->t_sra; A.srm1 = e->t_srm1; A.mean_noise = e->cfg.model_mean_type == 1;
   A.log_k = (float)log((double)e->cfg.num_classes);
   A.pos_noise = d_pos_noise; A.v_uniform = d_v_uniform; A.seed = seed;
   A.lig_pos = e->lig_pos.as<float4>(); A.lig_v = e->lig_v.as<int>();

@@ -68,7 +68,13 @@ __global__ void step_epilogue_kernel(TdStepArgs A) {
   // ---- positions: posterior mean + noise (reference :673-679)
   const int g = A.lig_graph[a];
   const float4 xt = A.lig_pos[a];
-  const float4 x0 = A.xm_final[A.lig_node[a]];
+  float4 x0 = A.xm_final[A.lig_node[a]];
+  if (A.mean_noise) {              // x0 = sqrt(1/ac) x_t - sqrt(1/ac - 1) (pred - x_t)   (reference :419-422,663-666)
+    const float ra = A.sra[t], rm = A.srm1[t];
+    x0.x = ra * xt.x - rm * (x0.x - xt.x);
+    x0.y = ra * xt.y - rm * (x0.y - xt.y);
+    x0.z = ra * xt.z - rm * (x0.z - xt.z);
+  }
   const float c0 = A.c0[t], ct = A.ct[t];
   const float sig = ((t == 0) ? 0.0f : 1.0f) * expf(0.5f * A.logvar[t]);
   float4 xn;

@@ -12,6 +12,8 @@ struct TdStepArgs {
   const float* logits;             // [Nl,K]
   const float4* offset;            // [B] pocket centroids
   const float *c0, *ct, *logvar;   // posterior_mean_c0_coef, posterior_mean_ct_coef, posterior_logvar [T]
+  const float *sra, *srm1;         // sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod [T] (model_mean_type 'noise')
+  int mean_noise;                  // 1: the network output is x_t + predicted noise direction (reference :663-666)
   const float *la_v, *l1ma_v, *lca_v, *l1mca_v;   // log_alphas_v, log_one_minus_alphas_v, and their cumprod versions [T]
   float log_k;                     // float32(np.log(num_classes))
   const float* pos_noise;          // tape [S,Nl,3] or NULL (Philox)

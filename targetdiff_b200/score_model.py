@@ -231,7 +231,8 @@ class ScorePosNet3D(nn.Module):
             keep.append((name, v))
             entries[i].name, entries[i].data, entries[i].numel = name, v.data_ptr(), v.numel()
         cfg = _lib.tdiff_config(self.hidden_dim, self.config.n_heads, self.config.num_layers, self.config.knn, self.config.num_r_gaussian,
-                                self.num_classes, self.protein_atom_feature_dim, self.num_timesteps)
+                                self.num_classes, self.protein_atom_feature_dim, self.num_timesteps,
+                                {'C0': 0, 'noise': 1}[self.model_mean_type])
         out = ctypes.c_void_p()
         _lib.check(lib.tdiff_create(ctypes.byref(cfg), entries, len(sd), index, ctypes.byref(out)))
         self._engine, self._engine_device, self._bound_key = out, index, None

@@ -215,3 +215,17 @@ def test_likelihood_estimation_vs_oracle_and_golden():
     # unseeded call: finite, one value per graph
     kp, kv = model.likelihood_estimation(*_args(b), time_step=t.to(DEV))
     assert kp.shape == kv.shape == (3,) and torch.isfinite(kp).all() and torch.isfinite(kv).all()
+
+
+def test_noise_mean_type_chain_vs_oracle():
+    """model_mean_type='noise' -- x0 is reconstructed from the predicted displacement in the step epilogue
+    (reference models/molopt_score_model.py:663-666, :419-422)."""
+    model, sd = _model(6, {'model_mean_type': 'noise'})
+    b = synth.make_batch(8, 3, n_protein=120, ligand_sizes=[8, 21, 13])
+    S = 6
+    pn, vu = synth.make_tape(7, S, len(b['batch_ligand']))
+    want = restate.sample_diffusion(sd, {'model_mean_type': 'noise'}, *_args(b, 'cpu'), pn, vu, num_steps=S)
+    got = model.sample_diffusion(*_args(b), num_steps=S, center_pos_mode='protein', noise_tape=(pn, vu))
+    assert torch.equal(torch.stack(got['v_traj']), torch.stack(want['v_traj']))
+    torch.testing.assert_close(torch.stack(got['pos_traj']), torch.stack(want['pos_traj']), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(torch.stack(got['v0_traj']), torch.stack(want['v0_traj']), rtol=0, atol=1e-3)

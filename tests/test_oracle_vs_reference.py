@@ -107,3 +107,23 @@ def test_likelihood_estimation_matches_reference(ref_model, steps):
     for w, g in zip(want, got):
         assert w.shape == g.shape == (2,)
         torch.testing.assert_close(g, w, rtol=1e-6, atol=1e-7)
+
+
+def test_sampling_chain_noise_mean_type_bit_exact():
+    """model_mean_type='noise' (reference models/molopt_score_model.py:663-666, :419-422)."""
+    ref = refload.import_reference()
+    cfg = refload.default_model_config()
+    cfg.update({'model_mean_type': 'noise'})
+    model = ref.ScorePosNet3D(cfg, synth.PROTEIN_FEATURE_DIM, synth.LIGAND_NUM_CLASSES).eval()
+    sd = synth.make_state_dict(6, schedules=restate.make_schedules())
+    model.load_state_dict(sd, strict=True)
+    b = synth.make_batch(8, 2, n_protein=48, ligand_sizes=[8, 6])
+    S = 3
+    pn, vu = synth.make_tape(7, S, len(b['batch_ligand']))
+    args = (b['protein_pos'], b['protein_v'], b['batch_protein'], b['init_ligand_pos'], b['init_ligand_v'], b['batch_ligand'])
+    with torch.no_grad(), refload.noise_tape(pn, vu):
+        want = model.sample_diffusion(*args, num_steps=S, center_pos_mode='protein')
+    got = restate.sample_diffusion(sd, {'model_mean_type': 'noise'}, *args, pn, vu, num_steps=S)
+    assert torch.equal(want['pos'], got['pos']) and torch.equal(want['v'], got['v'])
+    for k in ('pos_traj', 'v_traj', 'v0_traj', 'vt_traj'):
+        assert all(torch.equal(a, c) for a, c in zip(want[k], got[k])), k

@@ -75,10 +75,11 @@ struct tdiff_engine {
   // ---- batch
   bool bound = false, has_ligand = false, have_graph = false;
   bool restrict_last = false;           // sampling loop only: the last layer's x2h is evaluated for the relevant nodes only
+  bool knn_incremental = false;         // protein-protein neighbour keys cached at bind time (TDIFF_KNN_FULL=1 disables)
   bool have_prev = false;               // src_prev / etype / e_w hold the previous forward's graph of this batch (edge_const reuse)
   int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
   DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
-  DevBuf rel_flag, rel_list, n_rel, work_list, n_work;
+  DevBuf rel_flag, rel_list, n_rel, work_list, n_work, knn_cache;
   DevBuf xm0, xm1, offset, h0, h, P, q, src, src_prev, etype, e_w, dist, tslow, slow_list, n_slow, kbuf, vbuf, v16, lig_pos, lig_v, logits;
   DevBuf step, err_flag, node_off, total_edges;
   DevBuf stage[8];   // staging for tdiff_sample_host
@@ -418,7 +419,7 @@ extern "C" void tdiff_destroy(tdiff_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   DevBuf* bufs[] = {&e->node_ptr, &e->prot_ptr, &e->prot_node, &e->prot_graph, &e->lig_node, &e->lig_graph, &e->node_lig, &e->xm0, &e->xm1,
-                    &e->rel_flag, &e->rel_list, &e->n_rel, &e->work_list, &e->n_work, &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->src_prev, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->slow_list, &e->n_slow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
+                    &e->rel_flag, &e->rel_list, &e->n_rel, &e->work_list, &e->n_work, &e->knn_cache, &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->src_prev, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->slow_list, &e->n_slow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
                     &e->lig_v, &e->logits, &e->step, &e->err_flag, &e->node_off, &e->total_edges};
   for (auto* b : bufs) b->release();
   for (auto& b : e->stage) b.release();
@@ -468,6 +469,8 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   bad |= e->kbuf.ensure(slots * TD_H * 4) | e->vbuf.ensure(slots * TD_H * 4) | e->v16.ensure((size_t)Nl * K * TD_HEADS * 4 + 16);
   bad |= e->lig_pos.ensure(Nl * 16 + 16) | e->lig_v.ensure(Nl * 4 + 4) | e->logits.ensure((size_t)Nl * e->cfg.num_classes * 4 + 4);
   bad |= e->node_off.ensure(N * 8) | e->rel_flag.ensure(N + 16) | e->rel_list.ensure(N * 4 + 64) | e->n_rel.ensure(16) | e->work_list.ensure(N * 4 + 64) | e->n_work.ensure(16);
+  e->knn_incremental = !getenv("TDIFF_KNN_FULL") && Np > 0;
+  if (e->knn_incremental) bad |= e->knn_cache.ensure((size_t)N * (K + 1) * 8);
   if (bad) return set_err(TDIFF_ECUDA, "out of device memory binding a batch of %lld nodes (%zu edge slots)", N, slots);
   CK(cudaMemcpyAsync(e->node_ptr.p, node_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->prot_ptr.p, prot_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -490,6 +493,10 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
                           e->xm1.as<float4>(), st);
   td_launch_protein_embed(d_pfeat, (int)Np, e->cfg.protein_feat_dim, e->w_prot, e->b_prot, e->prot_node.as<int>(), e->h0.as<float>(), st);
   e->launches += 3;
+  if (e->knn_incremental) {      // protein atoms never move: their protein-only neighbour keys are computed once per bound batch
+    td_launch_knn_cache(e->xm0.as<float4>(), e->node_ptr.as<int>(), e->prot_ptr.as<int>(), B, max_ng, K, e->knn_cache.as<unsigned long long>(), st);
+    e->launches += 1;
+  }
   CK(cudaGetLastError());
   e->bound = true;
   return TDIFF_OK;
@@ -590,7 +597,10 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
   float* q = e->q.as<float>();
   td_launch_scatter_ligand_pos(e->lig_pos.as<float4>(), e->lig_node.as<int>(), Nl, xm[0], st);
   td_launch_init_h(e->h0.as<float>(), xm[0], e->lig_v.as<int>(), e->node_lig.as<int>(), e->wl_t, e->bl, N, h, st);
-  td_launch_knn(xm[0], e->node_ptr.as<int>(), e->B, e->max_ng, K, e->src.as<int>(), st);
+  if (e->knn_incremental)
+    td_launch_knn_update(xm[0], e->node_ptr.as<int>(), e->prot_ptr.as<int>(), e->B, e->max_ng, K, e->knn_cache.as<unsigned long long>(), e->src.as<int>(), st);
+  else
+    td_launch_knn(xm[0], e->node_ptr.as<int>(), e->B, e->max_ng, K, e->src.as<int>(), st);
   td_launch_edge_const(xm[0], src, e->src_prev.as<int>(), e->have_prev ? 1 : 0, N, K, e->ew_off, e->ew_coeff, e->ew_w1t, e->ew_b1, e->ew_g, e->ew_b, e->ew_w2, e->ew_b2,
                        e->etype.as<unsigned char>(), e->e_w.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), e->rel_flag.as<unsigned char>(),
                        e->work_list.as<int>(), e->n_work.as<int>(), st);

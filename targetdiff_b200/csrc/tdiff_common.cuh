@@ -111,6 +111,10 @@ __device__ __forceinline__ void tile_gemm_128(const float* __restrict__ As, cons
 
 // Launchers (defined in the .cu files, called by engine.cu).  All asynchronous on `st`.
 void td_launch_knn(const float4* xm, const int* node_ptr, int n_graphs, int max_nodes_per_graph, int k, int* src, cudaStream_t st);
+void td_launch_knn_cache(const float4* xm, const int* node_ptr, const int* prot_ptr, int n_graphs, int max_ng, int k, unsigned long long* cache,
+                         cudaStream_t st);
+void td_launch_knn_update(const float4* xm, const int* node_ptr, const int* prot_ptr, int n_graphs, int max_ng, int k,
+                          const unsigned long long* cache, int* src, cudaStream_t st);
 void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int have_prev, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
                           unsigned char* etype, float* e_w, int* slow_list, int* n_slow, unsigned char* rel_flag, int* work_list, int* n_work,

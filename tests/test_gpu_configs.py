@@ -229,3 +229,23 @@ def test_noise_mean_type_chain_vs_oracle():
     assert torch.equal(torch.stack(got['v_traj']), torch.stack(want['v_traj']))
     torch.testing.assert_close(torch.stack(got['pos_traj']), torch.stack(want['pos_traj']), rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(torch.stack(got['v0_traj']), torch.stack(want['v0_traj']), rtol=0, atol=1e-3)
+
+
+def test_incremental_knn_equals_full_scan(monkeypatch):
+    """The sampling loop's k-NN reuses cached protein-protein neighbour keys (protein atoms never move, reference
+    models/uni_transformer.py:205-206) and merges the ligand atoms per step; the neighbour lists -- hence the whole chain -- must be
+    bit-identical to the full per-step scan (TDIFF_KNN_FULL=1).  Ragged ligand sizes, a ligand-free and a tiny graph included."""
+    b = synth.make_batch(12, 5, n_protein=90, ligand_sizes=[20, 1, 33, 7, 45])
+    S = 8
+    pn, vu = synth.make_tape(3, S, int(b['init_ligand_pos'].shape[0]))
+    res = []
+    for full in ('', '1'):
+        if full:
+            monkeypatch.setenv('TDIFF_KNN_FULL', full)
+        model, _ = _model(2)
+        out = model.sample_diffusion(*_args(b), num_steps=S, center_pos_mode='protein', noise_tape=(pn, vu))
+        fwd = model(*_args(b))
+        res.append((out, fwd['edge_index']))
+    assert torch.equal(res[0][1], res[1][1])
+    assert torch.equal(res[0][0]['pos'], res[1][0]['pos']) and torch.equal(res[0][0]['v'], res[1][0]['v'])
+    assert torch.equal(torch.stack(res[0][0]['pos_traj']), torch.stack(res[1][0]['pos_traj']))

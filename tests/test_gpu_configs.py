@@ -234,7 +234,7 @@ def test_noise_mean_type_chain_vs_oracle():
 def test_incremental_knn_equals_full_scan(monkeypatch):
     """The sampling loop's k-NN reuses cached protein-protein neighbour keys (protein atoms never move, reference
     models/uni_transformer.py:205-206) and merges the ligand atoms per step; the neighbour lists -- hence the whole chain -- must be
-    bit-identical to the full per-step scan (TDIFF_KNN_FULL=1).  Ragged ligand sizes, a ligand-free and a tiny graph included."""
+    bit-identical to the full per-step scan (TDIFF_KNN_FULL=1).  Ragged ligand sizes incl. a single-atom ligand."""
     b = synth.make_batch(12, 5, n_protein=90, ligand_sizes=[20, 1, 33, 7, 45])
     S = 8
     pn, vu = synth.make_tape(3, S, int(b['init_ligand_pos'].shape[0]))

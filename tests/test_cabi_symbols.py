@@ -62,3 +62,29 @@ def test_state_dict_layout_and_unsupported_configs():
         c.update(bad)
         with pytest.raises(NotImplementedError):
             ScorePosNet3D(c, 27, 13)
+
+
+def test_config_struct_matches_header():
+    """The ctypes mirror of `tdiff_config` has the header's fields in the header's order and the same size (16 x int32)."""
+    from targetdiff_b200 import _lib
+    src = open(os.path.join(ROOT, 'include', 'tdiff.h')).read()
+    body = src[src.index('typedef struct tdiff_config {'):src.index('} tdiff_config;')]
+    fields = re.findall(r'^\s*int32_t\s+([a-z_]+)(\[(\d+)\])?;', body, flags=re.M)
+    names = [f[0] for f in fields]
+    words = sum(int(f[2]) if f[2] else 1 for f in fields)
+    assert names == [n for n, _ in _lib.tdiff_config._fields_]
+    assert ctypes.sizeof(_lib.tdiff_config) == 4 * words == 64
+    assert names.index('model_mean_type') == 8 and names[-1] == 'reserved'
+
+
+def test_model_mean_type_reaches_the_engine_config():
+    from targetdiff_b200.config import default_model_config
+    from targetdiff_b200.score_model import ScorePosNet3D
+    for name in ('C0', 'noise'):
+        c = default_model_config()
+        c.update({'model_mean_type': name})
+        assert ScorePosNet3D(c, 27, 13).model_mean_type == name
+    c = default_model_config()
+    c.update({'model_mean_type': 'x0'})
+    with pytest.raises(NotImplementedError):
+        ScorePosNet3D(c, 27, 13)

@@ -802,11 +802,165 @@ edge_slow_kernel(const int* __restrict__ src, const unsigned char* __restrict__ 
   }
 }
 
+
+// =====================================================================================================================
+// EXPERIMENTAL (off unless TDIFF_SLOW_TC=1; written at the end of round 1 without GPU time left to validate it -- see
+// DESIGN.md 6.1): the rare-type gaussian block on tensor cores.  Same arithmetic as the Dpre MMA of edge_mlp_v3_kernel
+// (G[128x32] . Tab_t^T, bf16 2-piece split, 3 products), but for tiles of 128 rows of ONE rare type t in {0,1,2} taken from
+// per-type slot lists, written to the row-indexed buffer edge_slow_kernel fills today.  Sequential phases per tile
+// (gaussians -> MMA -> TMEM read + store); 64 KB shared memory and 128 TMEM columns per CTA, so 3 CTAs share an SM.
+// =====================================================================================================================
+namespace v3 {
+constexpr int kPreThreads = 160;                       // warps 0-3: one thread per tile row; warp 4: MMA issuer + TMEM owner
+constexpr int oPT = 0, oPG = oPT + 3 * 2 * kGPiece, oPBar = oPG + 2 * kGPiece, kPreSmem = oPBar + 32;
+}
+
+// bucket the compact slow-slot list by edge type (order inside a bucket is irrelevant)
+__global__ void slow_bucket_kernel(const int* __restrict__ slow_list, const int* __restrict__ n_slow, const unsigned char* __restrict__ etype,
+                                   int* __restrict__ type_list, long long cap, int* __restrict__ n_type) {
+  const long long n = *n_slow;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int e = slow_list[i];
+    const int t = etype[e];
+    if (t < 3) type_list[(size_t)t * cap + atomicAdd(&n_type[t], 1)] = e;
+  }
+}
+void td_launch_slow_bucket(const int* slow_list, const int* n_slow, const unsigned char* etype, int* type_list, long long cap, int* n_type,
+                           int sm_count, cudaStream_t st) {
+  cudaMemsetAsync(n_type, 0, 3 * sizeof(int), st);
+  slow_bucket_kernel<<<sm_count * 4, 256, 0, st>>>(slow_list, n_slow, etype, type_list, cap, n_type);
+}
+
+__global__ void __launch_bounds__(v3::kPreThreads)
+edge_pre_tc_kernel(const int* __restrict__ type_list, long long cap, const int* __restrict__ n_type, int type_mask,
+                   const float* __restrict__ dist_arr, int k, const int* __restrict__ node_rank,
+                   const unsigned char* __restrict__ tab012_img /* 3 types x 3 pieces x 8 KB */, const float* __restrict__ offsets, float coeff,
+                   float* __restrict__ tslow) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  const uint32_t sT = sbase + oPT, sG = sbase + oPG, sBarA = sbase + oPBar;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem_raw + oPBar + 16);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ((sbase & 1023u) != 0) __trap();
+  // tables of the types this launch can meet: pieces 0 and 1 of each image
+  for (int t = 0; t < 3; ++t) {
+    if (!((type_mask >> t) & 1)) continue;
+    for (int i = tid; i < 2 * kGPiece / 16; i += kPreThreads) {
+      const uint4 v = reinterpret_cast<const uint4*>(tab012_img + (size_t)t * 3 * kGPiece)[i];
+      sts128(sT + (uint32_t)t * 2u * kGPiece + 16u * i, v.x, v.y, v.z, v.w);
+    }
+  }
+  if (tid == 0) {
+    mbar_init(sBarA, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(s_tmem), 128);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  long long tiles_of[3], n_of[3], total = 0;
+  for (int t = 0; t < 3; ++t) {
+    n_of[t] = ((type_mask >> t) & 1) ? (long long)n_type[t] : 0;
+    tiles_of[t] = (n_of[t] + 127) / 128;
+    total += tiles_of[t];
+  }
+  const float coeff2 = coeff * 1.4426950408889634f;
+  uint32_t phase = 0;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    int t = 0;
+    long long lt = tile;
+    while (lt >= tiles_of[t]) { lt -= tiles_of[t]; ++t; }
+    long long row = -1;
+    if (warp < 4) {
+      // ---- gaussian row of this thread's edge -> G (K slots: 8*c + i = gaussian 5*c + i, slot 29 = 1), bf16 split
+      const int r = tid;
+      const long long i = lt * 128 + r;
+      float dist = 0.f;
+      if (i < n_of[t]) {
+        const int e = type_list[(size_t)t * cap + i];
+        dist = dist_arr[e];
+        row = node_rank ? (long long)node_rank[e / k] * k + (e % k) : (long long)e;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float gv[8];
+#pragma unroll
+        for (int ii = 0; ii < 5; ++ii) {
+          const float d = dist - offsets[5 * c + ii];
+          gv[ii] = row >= 0 ? ex2_approx(coeff2 * (d * d)) : 0.0f;
+        }
+        gv[5] = (row >= 0 && c == 3) ? 1.0f : 0.0f;
+        gv[6] = gv[7] = 0.0f;
+        const uint32_t a0 = sG + (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u + (((uint32_t)c ^ (uint32_t)((r >> 1) & 3)) << 4);
+        split8_store(a0, a0 + kGPiece, gv);
+      }
+      fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+      tc_fence_after();
+      if (lane == 0) {
+        uint32_t accum = 0;
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const int pa_ = (term == 2) ? 1 : 0, pb_ = (term == 1) ? 1 : 0;      // a1b1, a1b2, a2b1
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            umma_bf16(tmem_base, desc_sw64(sG + pa_ * kGPiece + kk * 32), desc_sw64(sT + (uint32_t)t * 2u * kGPiece + pb_ * kGPiece + kk * 32),
+                      kIdesc, accum);
+            accum = 1;
+          }
+        }
+        umma_commit(sBarA);
+      }
+      __syncwarp();
+    } else {
+      mbar_wait(sBarA, phase);
+      tc_fence_after();
+      float* orow = tslow + (size_t)(row >= 0 ? row : 0) * TD_H;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        if (row >= 0) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8)
+            stg256(orow + c0 + c, __uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]),
+                   __uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]), __uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]));
+        }
+      }
+      tc_fence_before();
+    }
+    phase ^= 1u;
+    __syncthreads();                      // G and the accumulator are reused by the next tile
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+void td_launch_edge_pre_tc(const TdSlowTc& s, int type_mask, const int* node_rank, const float* dist, int k, const unsigned char* tab012_img,
+                           const float* offsets, float coeff, float* tslow, int sm_count, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(edge_pre_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreSmem);
+    configured = true;
+  }
+  edge_pre_tc_kernel<<<sm_count * 3, kPreThreads, kPreSmem, st>>>(s.type_list, s.cap, s.n_type, type_mask, dist, k, node_rank, tab012_img, offsets,
+                                                                 coeff, tslow);
+}
+
 void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_rows,
                            int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
                            const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const int* slow_list, const int* n_slow,
                            const float* qnode, float* out, const float* agg_logits, const float* agg_e_w, float* agg_h, int agg_n_nodes,
-                           const int* d_n_dst, int key_softmax, int sm_count, cudaStream_t st) {
+                           const int* d_n_dst, int key_softmax, const TdSlowTc* stc, int sm_count, cudaStream_t st) {
   if (n_rows == 0) return;
   LnParams lp;
   memcpy(lp.g, h_ln_g, sizeof(lp.g));
@@ -821,7 +975,11 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
   }
   const long long n_tiles = (n_rows + 127) / 128;
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
-  {
+  // experimental tensor-core pre-pass (TDIFF_SLOW_TC=1): full x2h launches (rows = slots) and h2x launches (rows = ligand rank * k + j)
+  const bool pre_tc = stc && stc->type_list && m.tab012_img && d_n_dst == nullptr && (row_nodes == nullptr || stc->node_rank != nullptr);
+  if (pre_tc) {
+    td_launch_edge_pre_tc(*stc, row_nodes ? 0x5 : 0x7, row_nodes ? stc->node_rank : nullptr, dist, k, m.tab012_img, offsets, coeff, tslow, sm_count, st);
+  } else {
     const bool listed = (row_nodes == nullptr) && slow_list;            // x2h: iterate the compacted list; h2x: scan the (few) rows
     long long blocks = (listed || d_n_dst) ? sm_count * 8 : (n_rows + 255) / 256;      // a block covers 256 rows per grid-stride iteration
     if (blocks > sm_count * 8) blocks = sm_count * 8;

@@ -75,11 +75,12 @@ struct tdiff_engine {
   // ---- batch
   bool bound = false, has_ligand = false, have_graph = false;
   bool restrict_last = false;           // sampling loop only: the last layer's x2h is evaluated for the relevant nodes only
+  bool slow_tc = false;                 // experimental: rare-type gaussian block on tensor cores (TDIFF_SLOW_TC=1)
   bool knn_incremental = false;         // protein-protein neighbour keys cached at bind time (TDIFF_KNN_FULL=1 disables)
   bool have_prev = false;               // src_prev / etype / e_w hold the previous forward's graph of this batch (edge_const reuse)
   int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
   DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
-  DevBuf rel_flag, rel_list, n_rel, work_list, n_work, knn_cache;
+  DevBuf rel_flag, rel_list, n_rel, work_list, n_work, knn_cache, type_list, n_type;
   DevBuf xm0, xm1, offset, h0, h, P, q, src, src_prev, etype, e_w, dist, tslow, slow_list, n_slow, kbuf, vbuf, v16, lig_pos, lig_v, logits;
   DevBuf step, err_flag, node_off, total_edges;
   DevBuf stage[8];   // staging for tdiff_sample_host
@@ -115,7 +116,7 @@ struct Packer {
   }
 };
 
-struct MlpOff { size_t tab, ln_g, ln_b, w2t, b2; int nout; long long img, tab3; };
+struct MlpOff { size_t tab, ln_g, ln_b, w2t, b2; int nout; long long img, tab3, tab012 = -1; };
 
 // round-to-nearest-even fp32 -> bf16 bit pattern
 inline uint16_t bf16_rn(float x) {
@@ -191,6 +192,11 @@ bool pack_edge_mlp(Packer& pk, const std::string& p, int nout, MlpOff& o, const 
     o.tab3 = (long long)pk.img.size();
     pk.img.resize(pk.img.size() + 3 * 8192, 0);
     pack_tab3_image(&pk.host[o.tab + (size_t)3 * TD_TAB * TD_H], pk.img, (size_t)o.tab3);
+    if (getenv("TDIFF_SLOW_TC")) {       // experimental tensor-core pre-pass for the rare edge types: images of types 0, 1, 2
+      o.tab012 = (long long)pk.img.size();
+      pk.img.resize(pk.img.size() + 3 * 3 * 8192, 0);
+      for (int t = 0; t < 3; ++t) pack_tab3_image(&pk.host[o.tab + (size_t)t * TD_TAB * TD_H], pk.img, (size_t)o.tab012 + (size_t)t * 3 * 8192);
+    }
   }
   *w1_out = w1;
   return true;
@@ -250,6 +256,7 @@ TdMlp mk_mlp(const float* base, const unsigned char* img_base, const MlpOff& o, 
   TdMlp m;
   m.w2_img = (o.img >= 0 && img_base) ? img_base + o.img : nullptr;
   m.tab3_img = (o.tab3 >= 0 && img_base) ? img_base + o.tab3 : nullptr;
+  m.tab012_img = (o.tab012 >= 0 && img_base) ? img_base + o.tab012 : nullptr;
   m.tab = base + o.tab; m.ln_g = base + o.ln_g; m.ln_b = base + o.ln_b; m.w2t = base + o.w2t; m.b2 = base + o.b2;
   m.nout = o.nout; m.offA = offA; m.offB = offB;
   return m;
@@ -419,7 +426,7 @@ extern "C" void tdiff_destroy(tdiff_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   DevBuf* bufs[] = {&e->node_ptr, &e->prot_ptr, &e->prot_node, &e->prot_graph, &e->lig_node, &e->lig_graph, &e->node_lig, &e->xm0, &e->xm1,
-                    &e->rel_flag, &e->rel_list, &e->n_rel, &e->work_list, &e->n_work, &e->knn_cache, &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->src_prev, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->slow_list, &e->n_slow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
+                    &e->rel_flag, &e->rel_list, &e->n_rel, &e->work_list, &e->n_work, &e->knn_cache, &e->type_list, &e->n_type, &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->src_prev, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->slow_list, &e->n_slow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
                     &e->lig_v, &e->logits, &e->step, &e->err_flag, &e->node_off, &e->total_edges};
   for (auto* b : bufs) b->release();
   for (auto& b : e->stage) b.release();
@@ -471,6 +478,8 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   bad |= e->node_off.ensure(N * 8) | e->rel_flag.ensure(N + 16) | e->rel_list.ensure(N * 4 + 64) | e->n_rel.ensure(16) | e->work_list.ensure(N * 4 + 64) | e->n_work.ensure(16);
   e->knn_incremental = !getenv("TDIFF_KNN_FULL") && Np > 0;
   if (e->knn_incremental) bad |= e->knn_cache.ensure((size_t)N * (K + 1) * 8);
+  e->slow_tc = getenv("TDIFF_SLOW_TC") != nullptr && e->mlp_mode == 2 && e->mlp_v3;
+  if (e->slow_tc) bad |= e->type_list.ensure(3 * slots * 4) | e->n_type.ensure(16);
   if (bad) return set_err(TDIFF_ECUDA, "out of device memory binding a batch of %lld nodes (%zu edge slots)", N, slots);
   CK(cudaMemcpyAsync(e->node_ptr.p, node_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->prot_ptr.p, prot_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -561,10 +570,12 @@ void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src,
               long long n_rows, int K, const TdMlp& m, const float* offsets, float coeff, float* out, cudaStream_t st,
               const float* qnode = nullptr, const float* agg_logits = nullptr, float* agg_h = nullptr, int agg_n = 0,
               const int* d_n_dst = nullptr, int key_softmax = 0) {
+  TdSlowTc stc = {e->slow_tc ? e->type_list.as<int>() : nullptr, (long long)e->N * K, e->n_type.as<int>(),
+                  row_nodes == e->lig_node.as<int>() ? e->node_lig.as<int>() : nullptr};
   if (e->mlp_mode == 2 && e->mlp_v3 && m.w2_img && m.tab3_img)
     td_launch_edge_mlp_v3(P, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, m.tab3_img, offsets, coeff,
                           e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena), e->host_arena.data() + (m.b2 - e->arena), e->tslow.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), qnode, out, agg_logits, e->e_w.as<float>(), agg_h, agg_n,
-                          d_n_dst, key_softmax, e->sm_count, st);
+                          d_n_dst, key_softmax, e->slow_tc ? &stc : nullptr, e->sm_count, st);
   else if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
     td_launch_edge_mlp_tc(P, xm, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, e->mlp_mode, offsets, coeff, out, e->sm_count, st);
   else
@@ -606,6 +617,10 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
                        e->work_list.as<int>(), e->n_work.as<int>(), st);
   td_launch_rel_compact(e->rel_flag.as<unsigned char>(), N, e->rel_list.as<int>(), e->n_rel.as<int>(), st);
   e->launches += 5;
+  if (e->slow_tc) {
+    td_launch_slow_bucket(e->slow_list.as<int>(), e->n_slow.as<int>(), etype, e->type_list.as<int>(), (long long)N * K, e->n_type.as<int>(), e->sm_count, st);
+    e->launches += 1;
+  }
   int cur = 0;
   for (size_t l = 0; l < e->layers.size(); ++l) {
     const TdLayer& ly = e->layers[l];

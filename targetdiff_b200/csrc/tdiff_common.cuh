@@ -30,6 +30,15 @@ struct TdMlp {
   int offA, offB;      // column offsets into the node projection P
   const unsigned char* w2_img;   // nout==128 edge MLPs: second Linear as 3 bf16 pieces in the UMMA K-major SWIZZLE_128B image
   const unsigned char* tab3_img; // type-3 (protein-protein) gaussian/type block [128 x 32] as bf16 pieces, K-major SWIZZLE_64B image
+  const unsigned char* tab012_img;   // same images for types 0, 1, 2 (3 x 24 KB), only packed with TDIFF_SLOW_TC=1, else NULL
+};
+
+// experimental tensor-core pre-pass for the rare edge types (edge_mlp_v3.cu, TDIFF_SLOW_TC=1)
+struct TdSlowTc {
+  const int* type_list;    // [3][cap] slots of type 0 / 1 / 2 (bucketed slow list)
+  long long cap;
+  const int* n_type;       // [3] device counts
+  const int* node_rank;    // node -> ligand rank (row = rank * k + j) for launches over the ligand destinations, else NULL
 };
 
 struct TdSubLayer {       // x2h or h2x
@@ -135,7 +144,9 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
                            int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
                            const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const int* slow_list, const int* n_slow,
                            const float* qnode, float* out, const float* agg_logits, const float* agg_e_w, float* agg_h, int agg_n_nodes,
-                           const int* d_n_dst, int key_softmax, int sm_count, cudaStream_t st);
+                           const int* d_n_dst, int key_softmax, const TdSlowTc* stc, int sm_count, cudaStream_t st);
+void td_launch_slow_bucket(const int* slow_list, const int* n_slow, const unsigned char* etype, int* type_list, long long cap, int* n_type,
+                           int sm_count, cudaStream_t st);
 void td_launch_rows_tc(int mode, const float* in, int ldi, int in_off, long long n_rows, TdMlp m, const unsigned char* w_image, int pieces, float* out,
                        int ldo, int nblocks, const int* row_list, const int* d_n_rows, int sm_count, cudaStream_t st);
 void td_launch_rel_compact(const unsigned char* flag, int n_nodes, int* rel_list, int* n_rel, cudaStream_t st);

@@ -24,6 +24,10 @@ from .sampling import sample_diffusion_ligand, seed_all
 from .score_model import ScorePosNet3D
 
 
+PROTEIN_FEATURE_DIM = 27                                                    # reference utils/transforms.py:115-132
+LIGAND_ATOM_MODE_CLASSES = {'basic': 8, 'add_aromatic': 13, 'full': 23}     # len(MAP_ATOM_TYPE_*_TO_INDEX), utils/transforms.py:11-66,143-149
+
+
 def build_result(data, outputs):
     pred_pos, pred_v, pred_pos_traj, pred_v_traj, pred_v0_traj, pred_vt_traj, time_list = outputs
     return {'data': data, 'pred_ligand_pos': pred_pos, 'pred_ligand_v': pred_v, 'pred_ligand_pos_traj': pred_pos_traj,
@@ -35,7 +39,17 @@ def _load_model(config, device, rank=0):
     (targetdiff_b200.dist.broadcast_state_dict) replaces the per-process checkpoint parsing of the reference's shell loop."""
     from . import dist as tdist
     ckpt = torch.load(config.model.checkpoint, map_location='cpu', weights_only=False)
-    model = ScorePosNet3D(ckpt['config'].model if hasattr(ckpt['config'], 'model') else ckpt['config']['model'], 27, 13)
+    tc = ckpt['config']
+    get = (lambda c, k: getattr(c, k)) if hasattr(tc, 'model') else (lambda c, k: c[k])
+    # feature widths come from the checkpoint's featurisers like the reference (scripts/sample_diffusion.py:140-160):
+    # protein = 6 elements + 20 residue types + backbone flag, ligand = class count of data.transform.ligand_atom_mode
+    try:
+        mode = get(get(get(tc, 'data'), 'transform'), 'ligand_atom_mode')
+    except (AttributeError, KeyError, TypeError):
+        mode = 'add_aromatic'
+    if mode not in LIGAND_ATOM_MODE_CLASSES:
+        raise NotImplementedError('checkpoint ligand_atom_mode=%r (known: %s)' % (mode, sorted(LIGAND_ATOM_MODE_CLASSES)))
+    model = ScorePosNet3D(get(tc, 'model'), PROTEIN_FEATURE_DIM, LIGAND_ATOM_MODE_CLASSES[mode])
     if rank == 0:
         model.load_state_dict(ckpt['model'])
     model = model.to(device)

@@ -128,8 +128,7 @@ void td_launch_edge_geom(const float4* xm, const int* src, int n_nodes, int k, f
   if (n > 0) edge_geom_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(xm, src, n, k, dist);
 }
 
-// Compact the relevant-node flags into a list (order irrelevant: every row is processed independently).  The list is padded to a
-// multiple of 4 entries with -1 so that a 128-row edge tile (k == 32) always holds 4 list entries.
+// Compact the relevant-node flags into a list (order irrelevant: every row is processed independently); consumers bound by *n_rel.
 __global__ void rel_compact_kernel(const unsigned char* __restrict__ flag, int n_nodes, int* __restrict__ rel_list, int* __restrict__ n_rel) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_nodes && flag[i]) rel_list[atomicAdd(n_rel, 1)] = i;

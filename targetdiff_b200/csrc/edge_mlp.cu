@@ -122,11 +122,8 @@ template <int NOUT>
 static void launch_impl(const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
                         long long n_rows, int k, TdMlp m, const float* offsets, float coeff, float* out, int sm_count, cudaStream_t st) {
   const size_t smem = (size_t)(128 * TD_LDA + 128 * NOUT + 4 * TD_TAB * TD_H + 2 * TD_H + NOUT) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(edge_mlp_kernel<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  static size_t opted[TD_MAX_DEVICES] = {0};
+  td_opt_in_smem(edge_mlp_kernel<NOUT>, smem, opted);
   long long n_tiles = (n_rows + 127) / 128;
   int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
   edge_mlp_kernel<NOUT><<<grid, TD_GEMM_THREADS, smem, st>>>(P, xm, src, etype, row_nodes, n_rows, k, m, offsets, coeff, out);

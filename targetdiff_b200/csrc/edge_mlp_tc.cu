@@ -479,11 +479,8 @@ static void launch_tc(const float* P, const float4* xm, const int* src, const un
                       long long n_rows, int k, TdMlp m, const unsigned char* w2_image, const float* offsets, float coeff, float* out, TcRows rw,
                       int nblocks, int sm_count, cudaStream_t st) {
   const size_t smem = 1024 + (size_t)NP * kPieceBytes + (size_t)NBUF * NP * kPieceBytes + 3 * TD_H * sizeof(float) + (2 * NBUF + 4) * 8 + 16;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(edge_mlp_tc_kernel<NP, NBUF, NSETS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  static size_t opted[TD_MAX_DEVICES] = {0};
+  td_opt_in_smem(edge_mlp_tc_kernel<NP, NBUF, NSETS, MODE>, smem, opted);
   const long long n_tiles = (n_rows + 127) / 128;
   int per = sm_count / nblocks;
   if (per < 1) per = 1;

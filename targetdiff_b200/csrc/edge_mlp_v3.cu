@@ -947,11 +947,8 @@ edge_pre_tc_kernel(const int* __restrict__ type_list, long long cap, const int* 
 
 void td_launch_edge_pre_tc(const TdSlowTc& s, int type_mask, const int* node_rank, const float* dist, int k, const unsigned char* tab012_img,
                            const float* offsets, float coeff, float* tslow, int sm_count, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(edge_pre_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreSmem);
-    configured = true;
-  }
+  static size_t opted[TD_MAX_DEVICES] = {0};
+  td_opt_in_smem(edge_pre_tc_kernel, kPreSmem, opted);
   edge_pre_tc_kernel<<<sm_count * 3, kPreThreads, kPreSmem, st>>>(s.type_list, s.cap, s.n_type, type_mask, dist, k, node_rank, tab012_img, offsets,
                                                                  coeff, tslow);
 }
@@ -967,12 +964,9 @@ void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* 
   memcpy(lp.b, h_ln_b, sizeof(lp.b));
   memset(lp.b2, 0, sizeof(lp.b2));
   memcpy(lp.b2, h_b2, sizeof(float) * (size_t)m.nout);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(edge_mlp_v3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(edge_mlp_v3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    configured = true;
-  }
+  static size_t opted128[TD_MAX_DEVICES] = {0}, opted16[TD_MAX_DEVICES] = {0};
+  td_opt_in_smem(edge_mlp_v3_kernel<128>, kSmem, opted128);
+  td_opt_in_smem(edge_mlp_v3_kernel<16>, kSmem, opted16);
   const long long n_tiles = (n_rows + 127) / 128;
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
   // experimental tensor-core pre-pass (TDIFF_SLOW_TC=1): full x2h launches (rows = slots) and h2x launches (rows = ligand rank * k + j)

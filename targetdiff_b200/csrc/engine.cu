@@ -78,6 +78,8 @@ struct tdiff_engine {
   bool slow_tc = false;                 // experimental: rare-type gaussian block on tensor cores (TDIFF_SLOW_TC=1)
   bool knn_incremental = false;         // protein-protein neighbour keys cached at bind time (TDIFF_KNN_FULL=1 disables)
   bool have_prev = false;               // src_prev / etype / e_w hold the previous forward's graph of this batch (edge_const reuse)
+  // developer switches, read from the environment ONCE in tdiff_create (never on the per-layer path)
+  bool env_no_fused_agg = false, env_no_restrict = false, env_no_graph = false, env_knn_full = false, env_slow_tc = false;
   int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
   DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
   DevBuf rel_flag, rel_list, n_rel, work_list, n_work, knn_cache, type_list, n_type;
@@ -387,6 +389,11 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     else if (!strcmp(mode, "tc6")) e->mlp_mode = 3;
     else { cudaFree(e->arena); cudaFree(e->img_arena); delete e; return set_err(TDIFF_EINVAL, "TDIFF_EDGE_MLP=%s (simt|tc3|tc3v2|tc6)", mode); }
   }
+  e->env_no_fused_agg = getenv("TDIFF_NO_FUSED_AGG") != nullptr;
+  e->env_no_restrict = getenv("TDIFF_NO_RESTRICT") != nullptr;
+  e->env_no_graph = getenv("TDIFF_NO_GRAPH") != nullptr;
+  e->env_knn_full = getenv("TDIFF_KNN_FULL") != nullptr;
+  e->env_slow_tc = getenv("TDIFF_SLOW_TC") != nullptr;
   e->host_arena = pk.host;
   const float* A = e->arena;
   const unsigned char* IM = e->img_arena;
@@ -476,9 +483,9 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   bad |= e->kbuf.ensure(slots * TD_H * 4) | e->vbuf.ensure(slots * TD_H * 4) | e->v16.ensure((size_t)Nl * K * TD_HEADS * 4 + 16);
   bad |= e->lig_pos.ensure(Nl * 16 + 16) | e->lig_v.ensure(Nl * 4 + 4) | e->logits.ensure((size_t)Nl * e->cfg.num_classes * 4 + 4);
   bad |= e->node_off.ensure(N * 8) | e->rel_flag.ensure(N + 16) | e->rel_list.ensure(N * 4 + 64) | e->n_rel.ensure(16) | e->work_list.ensure(N * 4 + 64) | e->n_work.ensure(16);
-  e->knn_incremental = !getenv("TDIFF_KNN_FULL") && Np > 0;
+  e->knn_incremental = !e->env_knn_full && Np > 0;
   if (e->knn_incremental) bad |= e->knn_cache.ensure((size_t)N * (K + 1) * 8);
-  e->slow_tc = getenv("TDIFF_SLOW_TC") != nullptr && e->mlp_mode == 2 && e->mlp_v3;
+  e->slow_tc = e->env_slow_tc && e->mlp_mode == 2 && e->mlp_v3;
   if (e->slow_tc) bad |= e->type_list.ensure(3 * slots * 4) | e->n_type.ensure(16);
   if (bad) return set_err(TDIFF_ECUDA, "out of device memory binding a batch of %lld nodes (%zu edge slots)", N, slots);
   CK(cudaMemcpyAsync(e->node_ptr.p, node_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -526,6 +533,7 @@ extern "C" int tdiff_set_ligand(tdiff_engine* e, const float* d_pos, const int64
     CK(cudaStreamSynchronize(st));
     if (flag) {
       cudaMemsetAsync(e->err_flag.p, 0, sizeof(int), st);
+      e->has_ligand = false;          // rejected indices were replaced by 0 (set_ligand_kernel); the state must be set again
       return set_err(TDIFF_EINVAL, "ligand atom type index >= num_classes (%d)", e->cfg.num_classes);
     }
   }
@@ -628,10 +636,10 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     node_side(e, h, N, ly.x2h, P, q, st);
     if (e->mlp_mode != 0) { td_launch_edge_geom(xm[cur], src, N, K, e->dist.as<float>(), st); e->launches += 1; }
     // k == 32: a 128-row tile is 4 complete destinations -> the value launch also performs the softmax aggregation (h += ...)
-    const bool fuse_agg = fused_logits(e) && K == 32 && !getenv("TDIFF_NO_FUSED_AGG");
+    const bool fuse_agg = fused_logits(e) && K == 32 && !e->env_no_fused_agg;
     // sampling loop, last layer: only the ligand atoms' features feed the type head and only ligand atoms + their neighbours feed
     // the last h2x, so x2h is evaluated for those destinations only (device-compacted list; final_h of other nodes is not produced)
-    const bool sub = fuse_agg && e->restrict_last && l + 1 == e->layers.size() && !getenv("TDIFF_NO_RESTRICT");
+    const bool sub = fuse_agg && e->restrict_last && l + 1 == e->layers.size() && !e->env_no_restrict;
     const int* rows = sub ? e->rel_list.as<int>() : nullptr;
     const int* d_n = sub ? e->n_rel.as<int>() : nullptr;
     {
@@ -650,7 +658,7 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     if (fix_x || Nl == 0) continue;     // h2x only moves ligand atoms; with fix_x its result is discarded (:204-206)
     // ---- h2x: x_lig <- x_lig + mean_heads sum_e alpha * v * e_w * (x_dst - x_src), destinations = ligand atoms only
     {
-      const bool rel = fused_logits(e) && !getenv("TDIFF_NO_RESTRICT");      // h2x only reads P / q of ligand atoms and their neighbours
+      const bool rel = fused_logits(e) && !e->env_no_restrict;      // h2x only reads P / q of ligand atoms and their neighbours
       node_side(e, h, N, ly.h2x, P, q, st, rel ? e->rel_list.as<int>() : nullptr, rel ? e->n_rel.as<int>() : nullptr);
     }
     {
@@ -772,7 +780,7 @@ extern "C" int tdiff_sample(tdiff_engine* e, int num_steps, const float* d_pos_n
   A.lig_pos = e->lig_pos.as<float4>(); A.lig_v = e->lig_v.as<int>();
   A.pos_traj = d_pos_traj; A.v_traj = (long long*)d_v_traj; A.v0_traj = d_v0_traj; A.vt_traj = d_vt_traj;
   CK(cudaMemsetAsync(e->step.p, 0, sizeof(int), st));
-  const bool eager = e->profiling || getenv("TDIFF_NO_GRAPH") != nullptr;
+  const bool eager = e->profiling || e->env_no_graph;
   Prof* total = new Prof(e, st, EV_TOTAL);
   // first step eagerly (module loading, shared-memory attributes), the rest replayed from one captured graph
   run_step(e, st, A);
@@ -832,7 +840,8 @@ extern "C" int tdiff_sample_host(tdiff_engine* e, int B, const int32_t* pc, cons
   if (h_pos_noise) bad |= sb[4].ensure(S * Nl * 12 + 16);
   if (h_v_uniform) bad |= sb[5].ensure(S * Nl * KC * 4 + 16);
   // trajectories share one staging block: pos [S,Nl,3] f32 | v [S,Nl] i64 | v0 [S,Nl,K] | vt [S,Nl,K]
-  const size_t o_pos = 0, o_v = o_pos + (h_pos_traj ? S * Nl * 12 : 0), o_v0 = (o_v + (h_v_traj ? S * Nl * 8 : 0) + 15) / 16 * 16,
+  const size_t o_pos = 0, o_v = (o_pos + (h_pos_traj ? S * Nl * 12 : 0) + 15) / 16 * 16,      // int64 rows need 8-byte alignment (S*Nl may be odd)
+               o_v0 = (o_v + (h_v_traj ? S * Nl * 8 : 0) + 15) / 16 * 16,
                o_vt = o_v0 + (h_v0_traj ? S * Nl * KC * 4 : 0), o_end = o_vt + (h_vt_traj ? S * Nl * KC * 4 : 0);
   bad |= sb[6].ensure(o_end + 16) | sb[7].ensure(Nl * 12 + Nl * 8 + 32);
   if (bad) return set_err(TDIFF_ECUDA, "out of device memory staging host buffers");

@@ -234,11 +234,8 @@ void td_launch_knn_cache(const float4* xm, const int* node_ptr, const int* prot_
   if (n_graphs <= 0) return;
   dim3 grid; size_t smem;
   knn_grid(n_graphs, max_ng, grid, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(knn_protein_cache_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static size_t opted[TD_MAX_DEVICES] = {0};
+  if (smem > 48 * 1024) td_opt_in_smem(knn_protein_cache_kernel, smem, opted);
   knn_protein_cache_kernel<<<grid, KNN_WARPS * 32, smem, st>>>(xm, node_ptr, prot_ptr, k, max_ng, cache);
 }
 
@@ -247,22 +244,16 @@ void td_launch_knn_update(const float4* xm, const int* node_ptr, const int* prot
   if (n_graphs <= 0) return;
   dim3 grid; size_t smem;
   knn_grid(n_graphs, max_ng, grid, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(knn_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static size_t opted[TD_MAX_DEVICES] = {0};
+  if (smem > 48 * 1024) td_opt_in_smem(knn_update_kernel, smem, opted);
   knn_update_kernel<<<grid, KNN_WARPS * 32, smem, st>>>(xm, node_ptr, prot_ptr, k, max_ng, cache, src);
 }
 
 void td_launch_knn(const float4* xm, const int* node_ptr, int n_graphs, int max_ng, int k, int* src, cudaStream_t st) {
   if (n_graphs <= 0) return;
   size_t smem = (size_t)max_ng * sizeof(float4) + (size_t)KNN_WARPS * max_ng * sizeof(unsigned long long);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static size_t opted[TD_MAX_DEVICES] = {0};
+  if (smem > 48 * 1024) td_opt_in_smem(knn_kernel, smem, opted);
   // enough chunks that small batches still fill the 148 SMs; each chunk re-stages the coordinates (cheap)
   int chunks = (max_ng + KNN_WARPS * 8 - 1) / (KNN_WARPS * 8);
   if (chunks < 1) chunks = 1;

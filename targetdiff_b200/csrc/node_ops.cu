@@ -96,11 +96,8 @@ node_proj_kernel(const float* __restrict__ h, int n_nodes, const float* __restri
 void td_launch_node_proj(const float* h, int n_nodes, const float* wn_t, const float* bn, float* P, cudaStream_t st) {
   if (n_nodes == 0) return;
   const size_t smem = (size_t)(128 * TD_LDA + 128 * 128) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(node_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  static size_t opted[TD_MAX_DEVICES] = {0};
+  td_opt_in_smem(node_proj_kernel, smem, opted);
   dim3 grid((n_nodes + 127) / 128, TD_NPROJ / 128);
   node_proj_kernel<<<grid, TD_GEMM_THREADS, smem, st>>>(h, n_nodes, wn_t, bn, P);
 }
@@ -147,11 +144,8 @@ node_q_kernel(const float* __restrict__ P, int n_nodes, TdMlp q, float* __restri
 void td_launch_node_q(const float* P, int n_nodes, TdMlp q, float* qout, cudaStream_t st) {
   if (n_nodes == 0) return;
   const size_t smem = (size_t)(128 * TD_LDA + 128 * 128) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(node_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  static size_t opted[TD_MAX_DEVICES] = {0};
+  td_opt_in_smem(node_q_kernel, smem, opted);
   node_q_kernel<<<(n_nodes + 127) / 128, TD_GEMM_THREADS, smem, st>>>(P, n_nodes, q, qout);
 }
 
@@ -203,11 +197,8 @@ void td_launch_head(const float* h, const int* lig_node, int n_lig, const float*
                     int n_classes, float* logits, cudaStream_t st) {
   if (n_lig == 0) return;
   const size_t smem = (size_t)(128 * 128 + HEAD_WARPS * TD_H) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  static size_t opted[TD_MAX_DEVICES] = {0};
+  td_opt_in_smem(head_kernel, smem, opted);
   int blocks = (n_lig + HEAD_WARPS - 1) / HEAD_WARPS;
   if (blocks > 148 * 2) blocks = 148 * 2;
   head_kernel<<<blocks, HEAD_WARPS * 32, smem, st>>>(h, lig_node, n_lig, w1t, b1, w2, b2, n_classes, logits);

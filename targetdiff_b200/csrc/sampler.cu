@@ -182,8 +182,8 @@ __global__ void set_ligand_kernel(const float* __restrict__ pos, const long long
   lig_pos[a] = make_float4(pos[3 * a] - o.x, pos[3 * a + 1] - o.y, pos[3 * a + 2] - o.z, 1.0f);
   if (v) {
     const long long vv = v[a];
-    if (vv < 0 || vv >= n_classes) atomicExch(err, 1);
-    lig_v[a] = (int)vv;
+    if (vv < 0 || vv >= n_classes) { atomicExch(err, 1); lig_v[a] = 0; }      // never store an index that would read out of bounds
+    else lig_v[a] = (int)vv;
   }
 }
 void td_launch_set_ligand(const float* pos, const long long* v, const int* lig_graph, const float4* offset, int apply_center, int n,

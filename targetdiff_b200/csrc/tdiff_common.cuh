@@ -15,7 +15,7 @@
 #define TD_TAB 21       // per edge type: 20 gaussian rows + 1 constant row (type column + bias)
 #define TD_KMAX 64      // max k of the k-NN graph
 #define TD_NPROJ 640    // node projection width: [A_k | A_v | B_k | B_v | q_pre]
-#define TD_CMAX 16      // max number of ligand classes held in registers by the step epilogue
+#define TD_CMAX 24      // max number of ligand classes held in registers by the step epilogue (ligand_atom_mode 'full' has 23)
 
 // One 2-layer edge/node MLP after the exact first-layer split:
 //   pre = P[dst, offA:] + P[src, offB:] + tab[type][20] + sum_j g_j * tab[type][j]      (edge MLPs)
@@ -116,6 +116,18 @@ __device__ __forceinline__ void tile_gemm_128(const float* __restrict__ As, cons
       }
     }
   }
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute (one process may own an engine on every GPU): each launcher
+// keeps, per kernel, the size it has already opted into on each device.
+#define TD_MAX_DEVICES 64
+template <class Kernel>
+inline void td_opt_in_smem(Kernel kernel, size_t bytes, size_t (&done)[TD_MAX_DEVICES]) {
+  int dev = 0;
+  const bool known = cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < TD_MAX_DEVICES;
+  if (known && bytes <= done[dev]) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (known) done[dev] = bytes;
 }
 
 // Launchers (defined in the .cu files, called by engine.cu).  All asynchronous on `st`.

@@ -407,6 +407,8 @@ class ScorePosNet3D(nn.Module):
             log_qT = self._q_v_pred(self._log_onehot(batch_ligand), last, batch_ligand)          # graph ids as types, as the reference (:573)
             kl_v = graph_mean((log_qT.exp() * (log_qT + math.log(K))).sum(1))
             return kl_pos, kl_v
+        if self.model_mean_type != 'C0':          # the reference raises here too (models/molopt_score_model.py:601-605); the prior branch above is mean-type free
+            raise ValueError('likelihood_estimation needs model_mean_type C0, got %r' % (self.model_mean_type,))
         if noise is None:
             pos_noise = torch.randn_like(x0)
             v_uniform = torch.rand(x0.shape[0], K, device=dev)

@@ -8,9 +8,12 @@ What a "step" is: one pass of the hot path -- one denoising step (k-NN graph + 9
 posterior update) over the whole in-flight batch.  Every step of the 1000-step chain costs the same (N and E = k*N do
 not change along the chain), so   molecules/sec = graphs_in_flight / (1000 * seconds_per_step).
 The timed K steps are consecutive steps of a real chain (Philox noise on the device), inputs resident in HBM.
-Workload (BASELINE.json configs[2], "synthetic CrossDocked-shape batch"): 64 distinct synthetic pockets x 10 samples =
-640 graphs of 300 protein + 20 ligand atoms per GPU, k=32, 9 layers, fp32.  Scaling is weak: every rank runs its own
-640-graph batch (pocket-sharded, no data-path collective; NCCL only broadcasts the weights once).
+Workload (default --workload cfg3 = BASELINE.json configs[2], "synthetic CrossDocked-shape batch"): 64 distinct synthetic pockets x
+10 samples = 640 graphs of 300 protein + 20 ligand atoms per GPU, k=32, 9 layers.  Scaling is weak: every rank runs its own batch
+(pocket-sharded, no data-path collective; NCCL only broadcasts the weights once).  Other presets: cfg1 (1 graph, 300+20), cfg2 (the
+1h36 pocket of tests/golden x 100 samples with prior-sampled ligand sizes), cfg5 (64 graphs of 1200+40 atoms, k=48).
+The timed region writes all four trajectories (positions, types, v0 / vt log-probabilities) like the reference's loop does;
+--full-chain times one REAL 1000-step chain (t = 999 ... 0) instead of K steps x 1000.
 """
 import argparse
 import json
@@ -24,6 +27,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CHAIN_STEPS = 1000
+# BASELINE.json `configs` as workload presets (per GPU)
+WORKLOADS = {
+    'cfg1': dict(pockets=1, samples=1, n_protein=300, n_ligand=20, knn=32),
+    'cfg2': dict(pockets=1, samples=100, n_protein=572, n_ligand=25, knn=32),
+    'cfg3': dict(pockets=64, samples=10, n_protein=300, n_ligand=20, knn=32),
+    'cfg5': dict(pockets=64, samples=1, n_protein=1200, n_ligand=40, knn=48),
+}
+DTYPE = 'f32 (storage, LayerNorm, softmax, accumulation); GEMM operands as 2-piece bf16 splits on tcgen05 (3 products, ~16-bit operand mantissa)'
 
 
 def parse_args():
@@ -32,23 +43,59 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--pockets', type=int, default=64)
-    ap.add_argument('--samples', type=int, default=10)
-    ap.add_argument('--n-protein', type=int, default=300)
-    ap.add_argument('--n-ligand', type=int, default=20)
-    ap.add_argument('--knn', type=int, default=32)
-    ap.add_argument('--e2e-steps', type=int, default=10, help='denoising steps per end-to-end public-API call')
+    ap.add_argument('--workload', default='cfg3', choices=sorted(WORKLOADS), help='BASELINE.json configuration preset')
+    ap.add_argument('--pockets', type=int)
+    ap.add_argument('--samples', type=int)
+    ap.add_argument('--n-protein', type=int)
+    ap.add_argument('--n-ligand', type=int)
+    ap.add_argument('--knn', type=int)
+    ap.add_argument('--full-chain', action='store_true', help='time one real 1000-step chain (overrides --steps)')
+    ap.add_argument('--e2e-steps', type=int, default=50, help='denoising steps per end-to-end public-API call')
     ap.add_argument('--profile-steps', type=int, default=3, help='eager steps timed per kernel with CUDA events for the roofline')
-    ap.add_argument('--cpu-graphs', type=int, default=4)
-    ap.add_argument('--cpu-steps', type=int, default=6)
+    ap.add_argument('--cpu-graphs', type=str, default='1,16', help='batch sizes of the CPU arm (BASELINE.md section 3: 1 and 16)')
+    ap.add_argument('--cpu-steps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    return ap.parse_args()
+    a = ap.parse_args()
+    for k, v in WORKLOADS[a.workload].items():
+        if getattr(a, k) is None:
+            setattr(a, k, v)
+    if a.full_chain:
+        a.steps = CHAIN_STEPS
+    return a
 
 
 def workload_name(a):
-    return 'cfg3: %d synthetic pockets x %d samples = %d graphs x (%d protein + %d ligand atoms), k=%d, 9 layers' % (
-        a.pockets, a.samples, a.pockets * a.samples, a.n_protein, a.n_ligand, a.knn)
+    what = 'the 1h36 pocket (tests/golden/1h36_pocket10.pdb, 572 atoms) x %d samples, prior-sampled ligand sizes' % a.samples \
+        if a.workload == 'cfg2' else '%d synthetic pockets x %d samples = %d graphs x (%d protein + %d ligand atoms)' % (
+            a.pockets, a.samples, a.pockets * a.samples, a.n_protein, a.n_ligand)
+    return '%s: %s, k=%d, 9 layers' % (a.workload, what, a.knn)
+
+
+def make_workload(a, rank):
+    """Host batch of this rank in the reference's calling convention + (graphs, nodes, ligand atoms)."""
+    import numpy as np
+    import torch
+    from oracle import synth
+    G = a.pockets * a.samples
+    if a.workload == 'cfg2':
+        from targetdiff_b200 import atom_num
+        from targetdiff_b200.pocket import pdb_to_pocket_data
+        data = pdb_to_pocket_data(os.path.join(ROOT, 'tests', 'golden', '1h36_pocket10.pdb'))
+        np.random.seed(2021 + rank)
+        size = atom_num.get_space_size(data.protein_pos.numpy())
+        sizes = [int(atom_num.sample_atom_num(size)) for _ in range(G)]
+        n_p = data.protein_pos.shape[0]
+        g = torch.Generator().manual_seed(2021 + rank)
+        bl = torch.repeat_interleave(torch.arange(G), torch.tensor(sizes))
+        b = dict(protein_pos=data.protein_pos.repeat(G, 1), protein_v=data.protein_atom_feature.float().repeat(G, 1),
+                 batch_protein=torch.repeat_interleave(torch.arange(G), n_p),
+                 init_ligand_pos=data.protein_pos.mean(0, keepdim=True) + torch.randn(len(bl), 3, generator=g),
+                 init_ligand_v=torch.randint(0, synth.LIGAND_NUM_CLASSES, (len(bl),), generator=g), batch_ligand=bl)
+        a.n_protein, a.n_ligand = n_p, round(sum(sizes) / G, 2)
+    else:
+        b = synth.make_batch(100 + rank, G, n_protein=a.n_protein, n_ligand=a.n_ligand, distinct_pockets=a.pockets)
+    return b, G, int(b['protein_pos'].shape[0] + b['init_ligand_pos'].shape[0]), int(b['init_ligand_pos'].shape[0])
 
 
 def measured_peaks():
@@ -127,7 +174,7 @@ def cpu_oracle_rate(a, graphs, steps, warmup=3):
     import torch
     from oracle import restate, synth
     sd = synth.make_state_dict(0, {'knn': a.knn}, schedules=restate.make_schedules())
-    b = synth.make_batch(1, graphs, n_protein=a.n_protein, n_ligand=a.n_ligand, distinct_pockets=graphs)
+    b = synth.make_batch(1, graphs, n_protein=a.n_protein, n_ligand=int(round(a.n_ligand)), distinct_pockets=graphs)
     cores = _best_thread_count(sd, a, b)
     torch.set_num_threads(cores)
     S = warmup + steps
@@ -144,12 +191,26 @@ def cpu_oracle_rate(a, graphs, steps, warmup=3):
     return rate, per_step, info
 
 
+def cpu_arm(a, steps, warmup=3):
+    """CPU arm at every batch size of --cpu-graphs (1 and 16); the best rate is the reported value."""
+    best = None
+    runs = []
+    for g in [max(1, int(x)) for x in str(a.cpu_graphs).split(',') if x.strip()]:
+        rate, per_step, info = cpu_oracle_rate(a, g, steps, warmup)
+        runs.append({'graphs': g, 'molecules_per_s': rate, 's_per_step': per_step, 'cores': info['cores']})
+        if best is None or rate > best[0]:
+            best = (rate, per_step, info)
+    rate, per_step, info = best
+    info['runs'] = runs
+    info['sample'] = 'best of batch sizes %s; ' % [r['graphs'] for r in runs] + info['sample']
+    return rate, per_step, info
+
+
 def run_reference_arm(a, rank, world):
     if rank != 0:
         return
-    graphs = max(1, a.cpu_graphs)
-    steps = max(1, a.steps)
-    rate, per_step, info = cpu_oracle_rate(a, graphs, steps, warmup=max(3, a.warmup))
+    steps = max(1, min(a.steps, 20))
+    rate, per_step, info = cpu_arm(a, steps, warmup=max(3, min(a.warmup, 5)))
     line = {'impl': 'reference', 'metric': 'molecules/sec (1000-step sampling, CrossDocked pocket shape)', 'value': rate, 'unit': 'molecules/s',
             'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -204,12 +265,9 @@ def main():
         model._drop_engine()
 
     # ---- synthetic batch of this rank (different pockets per rank), staged in pinned host memory
-    G = a.pockets * a.samples
-    b = synth.make_batch(100 + rank, G, n_protein=a.n_protein, n_ligand=a.n_ligand, distinct_pockets=a.pockets)
+    b, G, N, Nl = make_workload(a, rank)
     host = {k: v.pin_memory() for k, v in b.items()}
-    N = G * (a.n_protein + a.n_ligand)
     E = N * a.knn
-    Nl = G * a.n_ligand
     K = synth.LIGAND_NUM_CLASSES
 
     def to_dev():
@@ -222,8 +280,17 @@ def main():
     model._bind(eng, d['protein_pos'], d['protein_v'], d['batch_protein'], d['batch_ligand'], 1)
     _lib.check(lib.tdiff_set_ligand(eng, ctypes.c_void_p(d['init_ligand_pos'].data_ptr()), ctypes.c_void_p(d['init_ligand_v'].data_ptr()), 1, st))
 
+    # all four trajectories are written inside the timed region, like the reference's loop (models/molopt_score_model.py:687-693)
+    S_traj = max(a.steps, a.warmup, a.profile_steps, 3)
+    traj = (torch.empty(S_traj, Nl, 3, device=dev), torch.empty(S_traj, Nl, dtype=torch.int64, device=dev),
+            torch.empty(S_traj, Nl, K, device=dev), torch.empty(S_traj, Nl, K, device=dev))
+    PT = lambda t: ctypes.c_void_p(t.data_ptr())
+
     def chain(steps, seed):
-        _lib.check(lib.tdiff_sample(eng, steps, None, None, ctypes.c_uint64(seed), None, None, None, None, 0, st))
+        _lib.check(lib.tdiff_sample(eng, steps, None, None, ctypes.c_uint64(seed), PT(traj[0]), PT(traj[1]), PT(traj[2]), PT(traj[3]), 0, st))
+
+    def reset_state():
+        _lib.check(lib.tdiff_set_ligand(eng, ctypes.c_void_p(d['init_ligand_pos'].data_ptr()), ctypes.c_void_p(d['init_ligand_v'].data_ptr()), 1, st))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -233,6 +300,8 @@ def main():
 
     # ---- warm-up, then EXACTLY K timed denoising steps (device events, max over ranks)
     chain(max(3, a.warmup), 1)
+    if a.full_chain:
+        reset_state()                 # the real chain starts from the initial state at t = T - 1
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -299,8 +368,11 @@ def main():
             # tensor-core work actually executed by the edge MLPs of one layer (x2h: hk + hv on all E rows; h2x: xk + xv on ligand
             # destinations): per row 3 bf16 products x (128 x NOUT second Linear + 32 x 128 gaussian block) MAC on tcgen05
             El = Nl * a.knn
-            mac_row = lambda nout: 3 * (128 * nout + 32 * 128)
+            # (v4: the gaussian/type block of both edge types of a destination class is one K = 64 MMA: 2 x 21 useful slots of 64)
+            kpre = 64 if fused else 0
+            mac_row = lambda nout: 3 * (128 * nout + kpre * 128)
             flops = 2.0 * (E * 2 * mac_row(128) + El * (mac_row(128) + mac_row(16)))
+            useful = 2.0 * (E * 2 * 3 * (128 * 128 + 21 * 128) + El * 3 * (128 * 128 + 21 * 128 + 128 * 16 + 21 * 128))
             t_m = ms_mlp / (n_mlp / 2) * 1e-3                       # per layer (x2h pair + h2x pair, incl. the slow-row pre-passes)
             tpeak = None
             try:
@@ -309,17 +381,21 @@ def main():
             except Exception:
                 tpeak, tsrc = 1400.0, 'fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)'
             ach = flops / t_m / 1e12
-            mlp_traffic = None          # DRAM bytes of one value-MLP (+ aggregation) launch from the committed ncu --set full capture
+            # DRAM bytes of one value-MLP (+ aggregation) launch: not measurable inside this run (needs ncu); taken from this round's
+            # committed `ncu --set full` capture of the same workload when there is one, else null
+            mlp_traffic, traffic_src = None, None
             try:
-                tj = json.load(open(os.path.join(ROOT, 'profiles', 'edge_mlp_traffic.json')))
-                if tj.get('graphs') == G:
-                    mlp_traffic = tj['dram_bytes_per_launch']
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_edge_mlp_traffic.json')))
+                if tj.get('graphs') == G and tj.get('workload') == a.workload:
+                    mlp_traffic, traffic_src = tj['dram_bytes_per_launch'], 'profiles/r02_edge_mlp_traffic.json (ncu --set full, value launch)'
             except Exception:
                 pass
-            extra['edge_mlp'] = {'kernel': 'edge_mlp_v3_kernel x4 per layer (engine mode %d)' % mode, 'bound': 'tensor', 'achieved': ach, 'peak': tpeak,
-                                 'unit': 'TFLOP/s', 'frac': ach / tpeak, 'traffic': mlp_traffic, 'peak_source': tsrc, 'executed_flops_per_layer': flops,
+            extra['edge_mlp'] = {'kernel': 'edge_mlp_v4_kernel x4 per layer (engine mode %d)' % mode, 'bound': 'tensor', 'achieved': ach, 'peak': tpeak,
+                                 'unit': 'TFLOP/s', 'frac': ach / tpeak, 'traffic': mlp_traffic, 'traffic_source': traffic_src, 'peak_source': tsrc,
+                                 'executed_flops_per_layer': flops, 'useful_flops_per_layer': useful, 'frac_useful': useful / t_m / 1e12 / tpeak,
                                  'ms_per_layer': t_m * 1e3, 'share_of_step': ms_mlp / tot if tot else None,
-                                 'note': 'bf16-split products count as executed flops (3 MMAs per fp32-class product); the kernel is bound by its '
+                                 'note': 'executed flops = every issued tcgen05 MMA (3 bf16 products per fp32-class product, K = 64 gaussian block '
+                                         'incl. its zero padding); useful = the same without padding slots; the kernel is bound by its '
                                          'CUDA-core LayerNorm/split stage, see DESIGN.md section 6'}
             if roofline is None:            # aggregation fused into the value-MLP epilogue: the dominant kernel is the edge MLP itself
                 roofline = dict(extra['edge_mlp'])
@@ -362,10 +438,10 @@ def main():
     # ---- end to end through the public API with HOST buffers (H2D of the inputs, the chain, D2H of results + trajectories)
     e2e = None
     if not a.no_e2e:
-        S = max(3, a.e2e_steps)
+        S = CHAIN_STEPS if a.full_chain else max(3, a.e2e_steps)
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         d2h = Nl * 12 + Nl * 8 + S * Nl * (12 + 8 + 2 * K * 4)
-        reps = 2
+        reps = 1 if a.full_chain else 2
 
         def one_call(seed):
             dd = to_dev()
@@ -373,7 +449,8 @@ def main():
                                        dd['batch_ligand'], num_steps=S, center_pos_mode='protein', seed=seed, stack_traj=True)
             return r['pos'].cpu(), r['v'].cpu()
 
-        one_call(11)
+        if not a.full_chain:
+            one_call(11)
         barrier()
         t0 = time.perf_counter()
         for i in range(reps):
@@ -393,14 +470,16 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only; bounded sample)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        _, _, cpu = cpu_oracle_rate(a, a.cpu_graphs, a.cpu_steps)
+        _, _, cpu = cpu_arm(a, a.cpu_steps)
 
     if rank == 0:
         line = {'metric': 'molecules/sec (1000-step sampling, CrossDocked pocket shape)', 'value': value, 'unit': 'molecules/s', 'n_gpus': world,
                 'steps': a.steps, 'warmup': max(3, a.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'vs_baseline': None, 'dtype': DTYPE, 'data': 'synthetic',
                 'config': {'workload': workload_name(a), 'graphs_per_gpu': G, 'nodes': N, 'edges': E, 'chain_steps': CHAIN_STEPS,
-                           'step': 'one denoising step of the whole in-flight batch; value = graphs / (1000 * s_per_step)',
+                           'step': ('one REAL 1000-step chain (t = 999 ... 0) timed in full' if a.full_chain else
+                                    'one denoising step of the whole in-flight batch; value = graphs / (1000 * s_per_step)') +
+                                   '; all four trajectories written inside the timed region',
                            'parallelism': 'pocket-sharded x%d (no data-path collective)' % world,
                            'l2': 'per-step working set (k,v edge tensors %.1f GB) >> 126 MB L2; no explicit flush' % (2 * E * 512 / 1e9),
                            'noise': 'device Philox4x32-10'},

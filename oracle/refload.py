@@ -26,6 +26,18 @@ def import_reference():
     return importlib.import_module('models.molopt_score_model')
 
 
+def import_reference_scripts():
+    """The reference's sampling drivers, UNMODIFIED: returns (scripts.sample_diffusion, scripts.sample_for_pocket).
+    Needs, on top of the model shims, torch_geometric.data/transforms stand-ins and inert placeholders for the
+    import-only dependencies rdkit / openbabel / lmdb (oracle/shims/_absent.py)."""
+    import_reference()
+    import importlib
+    sys.path.insert(0, SHIMS) if SHIMS not in sys.path else None
+    import _absent
+    _absent.install()
+    return importlib.import_module('scripts.sample_diffusion'), importlib.import_module('scripts.sample_for_pocket')
+
+
 def default_model_config():
     """`configs/training.yml` model section (reference configs/training.yml:9-42) as an EasyDict."""
     import yaml

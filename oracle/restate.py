@@ -325,7 +325,7 @@ def forward(sd, cfg, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v
 # a4  the sampling loop                                        models/molopt_score_model.py:633-703
 # ----------------------------------------------------------------------------------------------
 def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand_pos, init_ligand_v, batch_ligand,
-                     pos_noise, v_uniform, num_steps=None, center_pos_mode='protein', step_callback=None):
+                     pos_noise, v_uniform, num_steps=None, center_pos_mode='protein', step_callback=None, pos_only=False):
     """Sampler (model_mean_type C0 or noise) driven by a noise tape: pos_noise [S,Nl,3], v_uniform [S,Nl,K].
     Returns the reference's dict ('pos','v','pos_traj','v_traj','v0_traj','vt_traj'), trajectories as lists."""
     cfg = dict(DEFAULT_MODEL_CONFIG, **(cfg or {}))
@@ -336,6 +336,10 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
         num_steps = T
     num_graphs = int(batch_protein.max()) + 1
     protein_pos, ligand_pos, offset = center_pos(protein_pos, init_ligand_pos, batch_protein, batch_ligand, center_pos_mode)
+    if not torch.is_tensor(offset):
+        # mode 'none' returns the float 0. (:118-119) and the reference's own `offset[batch_ligand]` (:691,695) then raises TypeError;
+        # the engine defines the obvious meaning (no shift), restated here so that the extension can be checked
+        offset = torch.zeros(num_graphs, 3)
     ligand_v = init_ligand_v
     pos_traj, v_traj, v0_traj, vt_traj = [], [], [], []
     time_seq = list(reversed(range(T - num_steps, T)))                                   # :649
@@ -351,17 +355,104 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
         logvar = extract(sd['posterior_logvar'], t, batch_ligand)                        # :674
         nonzero = (1 - (t == 0).float())[batch_ligand].unsqueeze(-1)                     # :676
         ligand_pos = pos_mean + nonzero * (0.5 * logvar).exp() * pos_noise[s]            # :677-679
-        log_v_recon = F.log_softmax(v0, dim=-1)                                          # :682
-        log_v = index_to_log_onehot(ligand_v, K)                                         # :683
-        log_model_prob = q_v_posterior(sd, log_v_recon, log_v, t, batch_ligand, K)       # :684
-        ligand_v = log_sample_categorical_from_uniform(log_model_prob, v_uniform[s])     # :685
-        v0_traj.append(log_v_recon.clone()); vt_traj.append(log_model_prob.clone())      # :687-688
+        if not pos_only:                                                                 # :681
+            log_v_recon = F.log_softmax(v0, dim=-1)                                      # :682
+            log_v = index_to_log_onehot(ligand_v, K)                                     # :683
+            log_model_prob = q_v_posterior(sd, log_v_recon, log_v, t, batch_ligand, K)   # :684
+            ligand_v = log_sample_categorical_from_uniform(log_model_prob, v_uniform[s])  # :685
+            v0_traj.append(log_v_recon.clone()); vt_traj.append(log_model_prob.clone())  # :687-688
         pos_traj.append((ligand_pos + offset[batch_ligand]).clone())                     # :691-692
         v_traj.append(ligand_v.clone())                                                  # :693
         if step_callback is not None:
             step_callback(s, i, preds, ligand_pos, ligand_v)
     return {'pos': ligand_pos + offset[batch_ligand], 'v': ligand_v, 'pos_traj': pos_traj, 'v_traj': v_traj,
             'v0_traj': v0_traj, 'vt_traj': vt_traj}
+
+
+# ----------------------------------------------------------------------------------------------
+# a1/a2  the sampling driver and the ligand-size prior    scripts/sample_diffusion.py:31-116; utils/evaluation/atom_num.py:9-26
+# ----------------------------------------------------------------------------------------------
+def get_space_size(pocket_3d_pos):
+    """utils/evaluation/atom_num.py:9-12: median of the 10 largest pairwise distances (scipy pdist, fp64)."""
+    from scipy import spatial as sc_spatial
+    d = sc_spatial.distance.pdist(pocket_3d_pos, metric='euclidean')
+    return np.median(np.sort(d)[::-1][:10])
+
+
+def sample_atom_num(space_size, prior):
+    """utils/evaluation/atom_num.py:15-26 on the empirical table `prior` = {'bounds': [...], 'bins': [{'num_atoms', 'prob'}, ...]}
+    (utils/evaluation/atom_num_config.py, a constant table); numpy's GLOBAL RNG like the reference."""
+    idx = len(prior['bounds'])
+    for i, b in enumerate(prior['bounds']):
+        if b > space_size:
+            idx = i
+            break
+    b = prior['bins'][idx]
+    return np.random.choice(b['num_atoms'], p=b['prob'])
+
+
+def sample_diffusion_ligand(sd, cfg, protein_pos, protein_atom_feature, num_samples, prior, batch_size=16, num_steps=None,
+                            pos_only=False, center_pos_mode='protein', sample_num_atoms='prior', ligand_v_full=None):
+    """scripts/sample_diffusion.py:31-116 on CPU.  Randomness comes from numpy's / torch's GLOBAL CPU generators in the reference's
+    order (seed them like utils/misc.py:58-61): per batch the size draws (:49), randn_like(center) (:63), rand_like(uniform logits)
+    (:69 -> models/molopt_score_model.py:161), then per step randn_like(pos) / rand_like(log prob) (models/molopt_score_model.py:678,685),
+    which are pre-drawn here in that interleaved order and handed to `sample_diffusion` as a tape.
+    Returns the reference's 7-tuple (positions float64 numpy, trajectories [steps, atoms, ...]); the time list holds zeros."""
+    c = dict(DEFAULT_MODEL_CONFIG, **(cfg or {}))
+    K = sd['ligand_atom_emb.weight'].shape[1]
+    T = sd['betas'].shape[0]
+    S = T if num_steps is None else num_steps
+    all_pos, all_v, all_pos_traj, all_v_traj, all_v0_traj, all_vt_traj, time_list = [], [], [], [], [], [], []
+    num_batch = int(np.ceil(num_samples / batch_size))                                   # :38
+    current_i = 0
+    n_prot = protein_pos.shape[0]
+    for i in range(num_batch):
+        n_data = batch_size if i < num_batch - 1 else num_samples - batch_size * (num_batch - 1)    # :41
+        batch_protein = torch.repeat_interleave(torch.arange(n_data), n_prot)            # Batch.from_data_list of n_data clones, :42
+        ppos = protein_pos.repeat(n_data, 1)
+        pfeat = protein_atom_feature.float().repeat(n_data, 1)
+        if sample_num_atoms == 'prior':                                                  # :47-50
+            pocket_size = get_space_size(protein_pos.detach().cpu().numpy())
+            sizes = [int(sample_atom_num(pocket_size, prior)) for _ in range(n_data)]
+        elif sample_num_atoms == 'range':                                                # :51-53
+            sizes = list(range(current_i + 1, current_i + n_data + 1))
+        else:
+            raise ValueError(sample_num_atoms)
+        batch_ligand = torch.repeat_interleave(torch.arange(n_data), torch.tensor(sizes))
+        s3 = torch.zeros(n_data, 3).index_add_(0, batch_protein, ppos)                   # scatter_mean, :61
+        center = s3 / torch.zeros(n_data).index_add_(0, batch_protein, torch.ones(len(batch_protein)))[:, None]
+        bc = center[batch_ligand]
+        init_pos = bc + torch.randn_like(bc)                                             # :63
+        if pos_only:
+            init_v = ligand_v_full.repeat(n_data)                                        # :67
+        else:
+            init_v = log_sample_categorical_from_uniform(torch.zeros(len(batch_ligand), K),
+                                                         torch.rand(len(batch_ligand), K))   # :69-70
+        pn = torch.empty(S, len(batch_ligand), 3)
+        vu = torch.zeros(S, len(batch_ligand), K)
+        for st in range(S):
+            pn[st] = torch.randn(len(batch_ligand), 3)
+            if not pos_only:
+                vu[st] = torch.rand(len(batch_ligand), K)
+        r = sample_diffusion(sd, c, ppos, pfeat, batch_protein, init_pos, init_v, batch_ligand, pn, vu, num_steps=num_steps,
+                             center_pos_mode=center_pos_mode, pos_only=pos_only)         # :72-82
+        cum = np.cumsum([0] + sizes)                                                     # :86
+        pos = r['pos'].numpy().astype(np.float64)
+        all_pos += [pos[cum[k]:cum[k + 1]] for k in range(n_data)]                       # :87-89
+        ptraj = torch.stack(r['pos_traj']).numpy().astype(np.float64)
+        all_pos_traj += [ptraj[:, cum[k]:cum[k + 1]] for k in range(n_data)]             # :91-98
+        v = r['v'].numpy()
+        all_v += [v[cum[k]:cum[k + 1]] for k in range(n_data)]                           # :101-102
+        vtraj = torch.stack(r['v_traj']).numpy()
+        all_v_traj += [vtraj[:, cum[k]:cum[k + 1]] for k in range(n_data)]               # :104-105
+        if not pos_only:                                                                 # :107-111
+            v0 = torch.stack(r['v0_traj']).numpy()
+            vt = torch.stack(r['vt_traj']).numpy()
+            all_v0_traj += [v0[:, cum[k]:cum[k + 1]] for k in range(n_data)]
+            all_vt_traj += [vt[:, cum[k]:cum[k + 1]] for k in range(n_data)]
+        time_list.append(0.0)
+        current_i += n_data
+    return all_pos, all_v, all_pos_traj, all_v_traj, all_v0_traj, all_vt_traj, time_list
 
 
 # ----------------------------------------------------------------------------------------------

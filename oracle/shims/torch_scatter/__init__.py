@@ -79,3 +79,18 @@ def scatter_softmax(src, index, dim=-1, dim_size=None):
     sum_per_index = scatter_sum(recentered_scores_exp, index, dim, dim_size=dim_size)
     normalizing_constants = sum_per_index.gather(dim, index)
     return recentered_scores_exp.div(normalizing_constants)
+
+
+def scatter(src, index, dim=-1, out=None, dim_size=None, reduce='sum'):
+    """torch_scatter.scatter dispatcher -- only imported by reference datasets/protein_ligand.py:10 (SDF parsing, not on the sampling path)."""
+    if reduce in ('sum', 'add'):
+        return scatter_sum(src, index, dim, out, dim_size)
+    if reduce == 'mean':
+        return scatter_mean(src, index, dim, out, dim_size)
+    if reduce == 'max':
+        return scatter_max(src, index, dim, out, dim_size)
+    raise NotImplementedError(reduce)
+
+
+def segment_coo(*args, **kwargs):
+    raise NotImplementedError('torch_scatter.segment_coo: only referenced by reference datasets/pl_data.py:61 (bond matrices), not on the sampling path')

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(EC_WARPS * 32)
 edge_gate_kernel(const float4* __restrict__ xm, const int* __restrict__ src, const int* __restrict__ work_list, const int* __restrict__ n_work,
                  int k, const float* __restrict__ offsets, float coeff, const float* __restrict__ w1t, const float* __restrict__ b1,
                  const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ w2, float b2,
-                 unsigned char* __restrict__ etype, float* __restrict__ e_w, int* __restrict__ slow_list, int* __restrict__ n_slow) {
+                 unsigned char* __restrict__ etype, float* __restrict__ e_w) {
   __shared__ float s_w1t[TD_NG * TD_H];
   __shared__ float s_b1[TD_H], s_g[TD_H], s_b[TD_H], s_w2[TD_H];
   for (int i = threadIdx.x; i < TD_NG * TD_H; i += blockDim.x) s_w1t[i] = w1t[i];
@@ -87,25 +87,20 @@ edge_gate_kernel(const float4* __restrict__ xm, const int* __restrict__ src, con
       const int ty = ns ? (nd ? 0 : 1) : (nd ? 2 : 3);
       etype[e] = (unsigned char)ty;
       e_w[e] = 1.0f / (1.0f + expf(-acc));
-      // every edge that touches a ligand atom (type != 3): compact list for edge_slow_kernel (order is irrelevant)
-      if (ty != 3 && slow_list) slow_list[atomicAdd(n_slow, 1)] = (int)e;
     }
   }
 }
 
 void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int have_prev, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
-                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, unsigned char* rel_flag, int* work_list, int* n_work,
-                          cudaStream_t st) {
+                          unsigned char* etype, float* e_w, unsigned char* rel_flag, int* work_list, int* n_work, cudaStream_t st) {
   if (n_nodes == 0) return;
   int blocks = (n_nodes + EC_WARPS - 1) / EC_WARPS;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  if (n_slow) cudaMemsetAsync(n_slow, 0, sizeof(int), st);
   if (rel_flag) cudaMemsetAsync(rel_flag, 0, (size_t)n_nodes, st);
   cudaMemsetAsync(n_work, 0, sizeof(int), st);
   edge_touch_kernel<<<blocks, EC_WARPS * 32, 0, st>>>(xm, src, src_prev, have_prev, n_nodes, k, rel_flag, work_list, n_work);
-  edge_gate_kernel<<<148 * 8, EC_WARPS * 32, 0, st>>>(xm, src, work_list, n_work, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2, etype, e_w,
-                                                     slow_list, n_slow);
+  edge_gate_kernel<<<148 * 8, EC_WARPS * 32, 0, st>>>(xm, src, work_list, n_work, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2, etype, e_w);
 }
 
 // Per-layer edge length |x_dst - x_src| (reference models/uni_transformer.py:188-189) for every slot, from the layer's input
@@ -137,4 +132,26 @@ void td_launch_rel_compact(const unsigned char* flag, int n_nodes, int* rel_list
   if (n_nodes == 0) return;
   cudaMemsetAsync(n_rel, 0, sizeof(int), st);
   rel_compact_kernel<<<(n_nodes + 255) / 256, 256, 0, st>>>(flag, n_nodes, rel_list, n_rel);
+}
+
+// Class-sorted list of the relevant destinations for the v4 edge kernel (last x2h of a sampling step): the relevant PROTEIN nodes,
+// padded with -1 to a multiple of `pad`, followed by the (already padded) list of all ligand nodes.  rel_counts = {entries, protein part}.
+__global__ void rel_rows_protein_kernel(const unsigned char* __restrict__ flag, const float4* __restrict__ xm, int n_nodes, int* __restrict__ rel_rows,
+                                        int* __restrict__ rel_counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_nodes && flag[i] && xm[i].w == 0.0f) rel_rows[atomicAdd(&rel_counts[2], 1)] = i;
+}
+__global__ void rel_rows_finish_kernel(const int* __restrict__ lig_rows, int n_lig_rows, int pad, int* __restrict__ rel_rows, int* __restrict__ rel_counts) {
+  const int n_p = rel_counts[2], n_pp = (n_p + pad - 1) / pad * pad;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pp - n_p) rel_rows[n_p + i] = -1;
+  if (i < n_lig_rows) rel_rows[n_pp + i] = lig_rows[i];
+  if (i == 0) { rel_counts[0] = n_pp + n_lig_rows; rel_counts[1] = n_pp; }
+}
+void td_launch_rel_rows(const unsigned char* rel_flag, const float4* xm, int n_nodes, const int* lig_rows, int n_lig_rows, int pad, int* rel_rows,
+                        int* rel_counts, cudaStream_t st) {
+  cudaMemsetAsync(rel_counts, 0, 4 * sizeof(int), st);
+  if (n_nodes > 0) rel_rows_protein_kernel<<<(n_nodes + 255) / 256, 256, 0, st>>>(rel_flag, xm, n_nodes, rel_rows, rel_counts);
+  const int n = n_lig_rows > pad ? n_lig_rows : pad;
+  rel_rows_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(lig_rows, n_lig_rows, pad, rel_rows, rel_counts);
 }

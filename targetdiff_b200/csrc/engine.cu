@@ -64,7 +64,7 @@ struct tdiff_engine {
   std::vector<float> host_arena;        // host copy of the packed fp32 weights (kernel-argument constants are read from it)
   unsigned char* img_arena = nullptr;   // bf16-split second-layer weights in the tensor-core shared-memory image
   int mlp_mode = 2;                     // 0: FP32 FFMA (edge_mlp.cu), 2: tcgen05 2-piece bf16 split / 3 products (default), 3: 3-piece / 6 products
-  bool mlp_v3 = true;                   // mode 2 edge MLPs: edge_mlp_v3.cu (both Linear layers on tcgen05) instead of edge_mlp_tc.cu
+  bool mlp_v4 = true;                   // mode 2 edge MLPs: edge_mlp_v4.cu (both Linear layers + every edge type's gaussian block on tcgen05) instead of edge_mlp_tc.cu
   std::vector<TdLayer> layers;
   const float *w_prot = nullptr, *b_prot = nullptr, *wl_t = nullptr, *bl = nullptr;
   const float *ew_w1t = nullptr, *ew_b1 = nullptr, *ew_g = nullptr, *ew_b = nullptr, *ew_w2 = nullptr, *ew_off = nullptr;
@@ -75,15 +75,18 @@ struct tdiff_engine {
   // ---- batch
   bool bound = false, has_ligand = false, have_graph = false;
   bool restrict_last = false;           // sampling loop only: the last layer's x2h is evaluated for the relevant nodes only
-  bool slow_tc = false;                 // experimental: rare-type gaussian block on tensor cores (TDIFF_SLOW_TC=1)
   bool knn_incremental = false;         // protein-protein neighbour keys cached at bind time (TDIFF_KNN_FULL=1 disables)
   bool have_prev = false;               // src_prev / etype / e_w hold the previous forward's graph of this batch (edge_const reuse)
   // developer switches, read from the environment ONCE in tdiff_create (never on the per-layer path)
-  bool env_no_fused_agg = false, env_no_restrict = false, env_no_graph = false, env_knn_full = false, env_slow_tc = false;
+  bool env_no_fused_agg = false, env_no_restrict = false, env_no_graph = false, env_knn_full = false;
   int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
   DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
-  DevBuf rel_flag, rel_list, n_rel, work_list, n_work, knn_cache, type_list, n_type;
-  DevBuf xm0, xm1, offset, h0, h, P, q, src, src_prev, etype, e_w, dist, tslow, slow_list, n_slow, kbuf, vbuf, v16, lig_pos, lig_v, logits;
+  DevBuf rel_flag, rel_list, n_rel, work_list, n_work, knn_cache;
+  // class-sorted destination lists of the v4 edge kernel: protein destinations (padded with -1 to `row_pad`), then ligand destinations
+  DevBuf x2h_rows, lig_rows, rel_rows, rel_counts;
+  long long x2h_n_dst = 0, x2h_split = 0, lig_n_dst = 0;
+  int row_pad = 4;                      // destinations per class are padded so that class boundaries fall on 128-row tile boundaries
+  DevBuf xm0, xm1, offset, h0, h, P, q, src, src_prev, etype, e_w, dist, kbuf, vbuf, v16, lig_pos, lig_v, logits;
   DevBuf step, err_flag, node_off, total_edges;
   DevBuf stage[8];   // staging for tdiff_sample_host
   // ---- instrumentation
@@ -118,7 +121,7 @@ struct Packer {
   }
 };
 
-struct MlpOff { size_t tab, ln_g, ln_b, w2t, b2; int nout; long long img, tab3, tab012 = -1; };
+struct MlpOff { size_t tab, ln_g, ln_b, w2t, b2; int nout; long long img, tabcls; };
 
 // round-to-nearest-even fp32 -> bf16 bit pattern
 inline uint16_t bf16_rn(float x) {
@@ -144,23 +147,27 @@ void pack_umma_image(const float* w2, std::vector<unsigned char>& img, size_t of
     }
 }
 
-// Type-3 gaussian/type block as the B operand of the small "pre" MMA of edge_mlp_v3.cu: [128 out (N) x 32 K-slots] bf16 pieces,
-// K-major SWIZZLE_64B (64-byte rows, 8-row groups of 512 B, 16-byte chunk index XOR (row/2)%4).
-// K slots: 8*c + i = gaussian 5*c + i (c < 4, i < 5), slot 29 = constant row (type column + bias), all other slots 0.
-void pack_tab3_image(const float* tab3 /*[21][128]*/, std::vector<unsigned char>& img, size_t off) {
-  for (int n = 0; n < 128; ++n)
-    for (int slot = 0; slot < 32; ++slot) {
-      int j = -1;
-      if ((slot & 7) < 5) j = 5 * (slot >> 3) + (slot & 7);
-      else if (slot == 29) j = 20;
-      float r = j >= 0 ? tab3[(size_t)j * 128 + n] : 0.0f;
-      const size_t o = (size_t)(n >> 3) * 512 + (size_t)(n & 7) * 64 + (size_t)((((slot >> 3)) ^ ((n >> 1) & 3)) * 16) + (size_t)(slot & 7) * 2;
-      for (int p = 0; p < 3; ++p) {
-        const uint16_t b = bf16_rn(r);
-        r = r - bf16_f(b);
-        memcpy(&img[off + (size_t)p * 8192 + o], &b, 2);
+// Gaussian/type blocks as the B operand of the small "pre" MMA of edge_mlp_v4.cu: per destination class one table of
+// [128 out (N) x 64 K-slots] in two bf16 pieces, K-major SWIZZLE_128B (128-byte rows, 16-byte chunk index XOR row % 8).
+// Class 0 (protein destination): slots 0-31 = type 3 (P->P), 32-63 = type 1 (L->P); class 1 (ligand destination): type 2 (P->L) / type 0 (L->L).
+// Inside a 32-slot half: 8*c + i = gaussian 5*c + i (c < 4, i < 5), slot 29 = constant row (type column + bias), all other slots 0.
+void pack_tabcls_image(const float* tab /*[4][21][128]*/, std::vector<unsigned char>& img, size_t off) {
+  static const int type_of[2][2] = {{3, 1}, {2, 0}};
+  for (int cls = 0; cls < 2; ++cls)
+    for (int n = 0; n < 128; ++n)
+      for (int slot = 0; slot < 64; ++slot) {
+        const int half = slot >> 5, sl = slot & 31;
+        int j = -1;
+        if ((sl & 7) < 5) j = 5 * (sl >> 3) + (sl & 7);
+        else if (sl == 29) j = 20;
+        float r = j >= 0 ? tab[((size_t)type_of[cls][half] * TD_TAB + j) * TD_H + n] : 0.0f;
+        const size_t o = (size_t)n * 128 + (size_t)(((slot >> 3) ^ (n & 7)) * 16) + (size_t)(slot & 7) * 2;
+        for (int p = 0; p < 2; ++p) {
+          const uint16_t b = bf16_rn(r);
+          r = r - bf16_f(b);
+          memcpy(&img[off + (size_t)cls * 32768 + (size_t)p * 16384 + o], &b, 2);
+        }
       }
-    }
 }
 
 // edge MLP: first Linear [128, 4 + 80 + 128 + 128] split, LayerNorm affine, second Linear transposed
@@ -186,19 +193,14 @@ bool pack_edge_mlp(Packer& pk, const std::string& p, int nout, MlpOff& o, const 
   for (int kk = 0; kk < TD_H; ++kk)
     for (int n = 0; n < nout; ++n) pk.host[o.w2t + (size_t)kk * nout + n] = w2[(size_t)n * TD_H + kk];
   o.b2 = pk.alloc(nout); memcpy(&pk.host[o.b2], b2, nout * sizeof(float));
-  o.img = -1; o.tab3 = -1;
+  o.img = -1; o.tabcls = -1;
   if (nout == TD_H || nout == 16) {
     o.img = (long long)pk.img.size();
     pk.img.resize(pk.img.size() + 3 * (size_t)nout * 256, 0);
     pack_umma_image(w2, pk.img, (size_t)o.img, nout);
-    o.tab3 = (long long)pk.img.size();
-    pk.img.resize(pk.img.size() + 3 * 8192, 0);
-    pack_tab3_image(&pk.host[o.tab + (size_t)3 * TD_TAB * TD_H], pk.img, (size_t)o.tab3);
-    if (getenv("TDIFF_SLOW_TC")) {       // experimental tensor-core pre-pass for the rare edge types: images of types 0, 1, 2
-      o.tab012 = (long long)pk.img.size();
-      pk.img.resize(pk.img.size() + 3 * 3 * 8192, 0);
-      for (int t = 0; t < 3; ++t) pack_tab3_image(&pk.host[o.tab + (size_t)t * TD_TAB * TD_H], pk.img, (size_t)o.tab012 + (size_t)t * 3 * 8192);
-    }
+    o.tabcls = (long long)pk.img.size();
+    pk.img.resize(pk.img.size() + 2 * 32768, 0);
+    pack_tabcls_image(&pk.host[o.tab], pk.img, (size_t)o.tabcls);
   }
   *w1_out = w1;
   return true;
@@ -219,7 +221,7 @@ bool pack_sublayer(Packer& pk, const std::string& p, const char* kn, const char*
   const float* w2q = pk.get(qp + ".net.3.weight", (int64_t)TD_H * TD_H);
   const float* b2q = pk.get(qp + ".net.3.bias", TD_H);
   if (!w1q || !b1q || !gq || !bq || !w2q || !b2q) return false;
-  so.q.nout = TD_H; so.q.tab = 0; so.q.tab3 = -1;
+  so.q.nout = TD_H; so.q.tab = 0; so.q.tabcls = -1;
   so.q.img = (long long)pk.img.size();
   pk.img.resize(pk.img.size() + 3 * 32768, 0);
   pack_umma_image(w2q, pk.img, (size_t)so.q.img);
@@ -257,8 +259,7 @@ bool pack_sublayer(Packer& pk, const std::string& p, const char* kn, const char*
 TdMlp mk_mlp(const float* base, const unsigned char* img_base, const MlpOff& o, int offA, int offB) {
   TdMlp m;
   m.w2_img = (o.img >= 0 && img_base) ? img_base + o.img : nullptr;
-  m.tab3_img = (o.tab3 >= 0 && img_base) ? img_base + o.tab3 : nullptr;
-  m.tab012_img = (o.tab012 >= 0 && img_base) ? img_base + o.tab012 : nullptr;
+  m.tabcls_img = (o.tabcls >= 0 && img_base) ? img_base + o.tabcls : nullptr;
   m.tab = base + o.tab; m.ln_g = base + o.ln_g; m.ln_b = base + o.ln_b; m.w2t = base + o.w2t; m.b2 = base + o.b2;
   m.nout = o.nout; m.offA = offA; m.offB = offB;
   return m;
@@ -385,7 +386,7 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
   if (const char* mode = getenv("TDIFF_EDGE_MLP")) {
     if (!strcmp(mode, "simt")) e->mlp_mode = 0;
     else if (!strcmp(mode, "tc3")) e->mlp_mode = 2;
-    else if (!strcmp(mode, "tc3v2")) { e->mlp_mode = 2; e->mlp_v3 = false; }
+    else if (!strcmp(mode, "tc3v2")) { e->mlp_mode = 2; e->mlp_v4 = false; }
     else if (!strcmp(mode, "tc6")) e->mlp_mode = 3;
     else { cudaFree(e->arena); cudaFree(e->img_arena); delete e; return set_err(TDIFF_EINVAL, "TDIFF_EDGE_MLP=%s (simt|tc3|tc3v2|tc6)", mode); }
   }
@@ -393,7 +394,6 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
   e->env_no_restrict = getenv("TDIFF_NO_RESTRICT") != nullptr;
   e->env_no_graph = getenv("TDIFF_NO_GRAPH") != nullptr;
   e->env_knn_full = getenv("TDIFF_KNN_FULL") != nullptr;
-  e->env_slow_tc = getenv("TDIFF_SLOW_TC") != nullptr;
   e->host_arena = pk.host;
   const float* A = e->arena;
   const unsigned char* IM = e->img_arena;
@@ -433,7 +433,7 @@ extern "C" void tdiff_destroy(tdiff_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   DevBuf* bufs[] = {&e->node_ptr, &e->prot_ptr, &e->prot_node, &e->prot_graph, &e->lig_node, &e->lig_graph, &e->node_lig, &e->xm0, &e->xm1,
-                    &e->rel_flag, &e->rel_list, &e->n_rel, &e->work_list, &e->n_work, &e->knn_cache, &e->type_list, &e->n_type, &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->src_prev, &e->etype, &e->e_w, &e->dist, &e->tslow, &e->slow_list, &e->n_slow, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
+                    &e->rel_flag, &e->rel_list, &e->n_rel, &e->work_list, &e->n_work, &e->knn_cache, &e->x2h_rows, &e->lig_rows, &e->rel_rows, &e->rel_counts, &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->src_prev, &e->etype, &e->e_w, &e->dist, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
                     &e->lig_v, &e->logits, &e->step, &e->err_flag, &e->node_off, &e->total_edges};
   for (auto* b : bufs) b->release();
   for (auto& b : e->stage) b.release();
@@ -479,14 +479,28 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   bad |= e->xm0.ensure(N * 16) | e->xm1.ensure(N * 16) | e->offset.ensure((size_t)B * 16);
   bad |= e->h0.ensure(N * TD_H * 4) | e->h.ensure(N * TD_H * 4) | e->P.ensure((size_t)N * TD_NPROJ * 4) | e->q.ensure(N * TD_H * 4);
   bad |= e->src.ensure(slots * 4) | e->src_prev.ensure(slots * 4) | e->etype.ensure(slots) | e->e_w.ensure(slots * 4) | e->dist.ensure(slots * 4);
-  if (e->mlp_mode == 2 && e->mlp_v3) bad |= e->tslow.ensure(slots * TD_H * 4) | e->slow_list.ensure(slots * 4) | e->n_slow.ensure(16);   // row-indexed, only ligand-touching rows are touched
-  bad |= e->kbuf.ensure(slots * TD_H * 4) | e->vbuf.ensure(slots * TD_H * 4) | e->v16.ensure((size_t)Nl * K * TD_HEADS * 4 + 16);
+  // class-sorted destination lists (v4 edge kernel): each class padded so that its rows end on a 128-row tile boundary
+  const bool v4 = e->mlp_mode == 2 && e->mlp_v4;
+  int gcd128 = 128;
+  while (K % gcd128) gcd128 >>= 1;
+  e->row_pad = 128 / gcd128;
+  const long long pad = e->row_pad, nPpad = (Np + pad - 1) / pad * pad, nLpad = (Nl + pad - 1) / pad * pad;
+  e->x2h_n_dst = nPpad + nLpad; e->x2h_split = nPpad; e->lig_n_dst = nLpad;
+  std::vector<int> x2h_rows((size_t)(nPpad + nLpad), -1), lig_rows((size_t)nLpad, -1);
+  for (long long i = 0; i < Np; ++i) x2h_rows[i] = prot_node[i];
+  for (long long i = 0; i < Nl; ++i) { x2h_rows[nPpad + i] = lig_node[i]; lig_rows[i] = lig_node[i]; }
+  if (v4) bad |= e->x2h_rows.ensure(x2h_rows.size() * 4 + 4) | e->lig_rows.ensure(lig_rows.size() * 4 + 4) | e->rel_rows.ensure(x2h_rows.size() * 4 + 4) |
+                 e->rel_counts.ensure(16);
+  // per-edge buffers: v4 keeps 16 attention logits / weights per row and, with the aggregation fused into the value launch (k == 32),
+  // no [E,128] tensor at all; the earlier execution modes materialise keys and values
+  const bool fuse = v4 && K == 32 && !e->env_no_fused_agg;
+  bad |= e->kbuf.ensure(v4 ? (size_t)(nPpad + nLpad) * K * TD_HEADS * 4 + 64 : slots * TD_H * 4);
+  if (!fuse) bad |= e->vbuf.ensure(slots * TD_H * 4);
+  bad |= e->v16.ensure((size_t)nLpad * K * TD_HEADS * 4 + 16);
   bad |= e->lig_pos.ensure(Nl * 16 + 16) | e->lig_v.ensure(Nl * 4 + 4) | e->logits.ensure((size_t)Nl * e->cfg.num_classes * 4 + 4);
   bad |= e->node_off.ensure(N * 8) | e->rel_flag.ensure(N + 16) | e->rel_list.ensure(N * 4 + 64) | e->n_rel.ensure(16) | e->work_list.ensure(N * 4 + 64) | e->n_work.ensure(16);
   e->knn_incremental = !e->env_knn_full && Np > 0;
   if (e->knn_incremental) bad |= e->knn_cache.ensure((size_t)N * (K + 1) * 8);
-  e->slow_tc = e->env_slow_tc && e->mlp_mode == 2 && e->mlp_v3;
-  if (e->slow_tc) bad |= e->type_list.ensure(3 * slots * 4) | e->n_type.ensure(16);
   if (bad) return set_err(TDIFF_ECUDA, "out of device memory binding a batch of %lld nodes (%zu edge slots)", N, slots);
   CK(cudaMemcpyAsync(e->node_ptr.p, node_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->prot_ptr.p, prot_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -499,6 +513,10 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
     CK(cudaMemcpyAsync(e->lig_graph.p, lig_graph.data(), Nl * 4, cudaMemcpyHostToDevice, st));
   }
   CK(cudaMemcpyAsync(e->node_lig.p, node_lig.data(), N * 4, cudaMemcpyHostToDevice, st));
+  if (v4) {
+    if (!x2h_rows.empty()) CK(cudaMemcpyAsync(e->x2h_rows.p, x2h_rows.data(), x2h_rows.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!lig_rows.empty()) CK(cudaMemcpyAsync(e->lig_rows.p, lig_rows.data(), lig_rows.size() * 4, cudaMemcpyHostToDevice, st));
+  }
   CK(cudaStreamSynchronize(st));   // host vectors go out of scope
   CK(cudaMemsetAsync(e->offset.p, 0, (size_t)B * 16, st));
   CK(cudaMemsetAsync(e->h0.p, 0, (size_t)N * TD_H * 4, st));
@@ -571,20 +589,30 @@ struct Prof {
   ~Prof() { if (on) { cudaEventRecord(ev.b, st); e->events.push_back(ev); } }
 };
 
-// per-edge MLP dispatch: tensor-core path for the 128-wide MLPs (hk, hv, xk), FFMA path for xv (16 outputs) or when forced
-// `qnode` != NULL (v3 path only): the MLP is a key MLP and `out` receives the 16 attention logits per row instead of the 128 keys
-bool fused_logits(const tdiff_engine* e) { return e->mlp_mode == 2 && e->mlp_v3; }
-void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
-              long long n_rows, int K, const TdMlp& m, const float* offsets, float coeff, float* out, cudaStream_t st,
-              const float* qnode = nullptr, const float* agg_logits = nullptr, float* agg_h = nullptr, int agg_n = 0,
-              const int* d_n_dst = nullptr, int key_softmax = 0) {
-  TdSlowTc stc = {e->slow_tc ? e->type_list.as<int>() : nullptr, (long long)e->N * K, e->n_type.as<int>(),
-                  row_nodes == e->lig_node.as<int>() ? e->node_lig.as<int>() : nullptr};
-  if (e->mlp_mode == 2 && e->mlp_v3 && m.w2_img && m.tab3_img)
-    td_launch_edge_mlp_v3(P, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, m.tab3_img, offsets, coeff,
-                          e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena), e->host_arena.data() + (m.b2 - e->arena), e->tslow.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), qnode, out, agg_logits, e->e_w.as<float>(), agg_h, agg_n,
-                          d_n_dst, key_softmax, e->slow_tc ? &stc : nullptr, e->sm_count, st);
-  else if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
+// per-edge MLP dispatch.  `list`: which destination set the launch covers.
+//   v4 (default): class-sorted destination lists; `qnode` != NULL marks a key MLP whose output is 16 attention logits (or, with
+//   `key_softmax`, softmax weights * e_w) per row; `agg_logits` / `agg_h` make the value launch perform the attention aggregation.
+//   earlier modes: tcgen05 second Linear with keys / values in HBM (edge_mlp_tc.cu) or the FP32 FFMA build (edge_mlp.cu).
+enum RowList { ROWS_ALL = 0, ROWS_LIGAND = 1, ROWS_RELEVANT = 2 };
+bool fused_logits(const tdiff_engine* e) { return e->mlp_mode == 2 && e->mlp_v4; }
+void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src, const unsigned char* etype, RowList list, int K, const TdMlp& m,
+              const float* offsets, float coeff, float* out, cudaStream_t st, const float* qnode = nullptr, const float* agg_logits = nullptr,
+              float* agg_h = nullptr, int key_softmax = 0) {
+  if (fused_logits(e) && m.w2_img && m.tabcls_img) {
+    const int* rows = list == ROWS_ALL ? e->x2h_rows.as<int>() : list == ROWS_LIGAND ? e->lig_rows.as<int>() : e->rel_rows.as<int>();
+    const long long n_dst = list == ROWS_LIGAND ? e->lig_n_dst : e->x2h_n_dst;          // ROWS_RELEVANT: upper bound, real counts on the device
+    const long long split = list == ROWS_LIGAND ? 0 : e->x2h_split;
+    // plain (unfused) x2h outputs are consumed by slot index (aggregate_h_logits_kernel); everything else by row index
+    const int by_slot = (list != ROWS_LIGAND && !key_softmax && agg_logits == nullptr) ? 1 : 0;
+    td_launch_edge_mlp_v4(P, src, etype, e->dist.as<float>(), rows, n_dst, split, list == ROWS_RELEVANT ? e->rel_counts.as<int>() : nullptr, K, m,
+                          offsets, coeff, e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena),
+                          e->host_arena.data() + (m.b2 - e->arena), qnode, out, by_slot, agg_logits, e->e_w.as<float>(), agg_h, key_softmax,
+                          e->sm_count, st);
+    return;
+  }
+  const int* row_nodes = list == ROWS_LIGAND ? e->lig_node.as<int>() : nullptr;
+  const long long n_rows = (long long)(list == ROWS_LIGAND ? e->Nl : e->N) * K;
+  if (e->mlp_mode != 0 && m.nout == TD_H && m.w2_img)
     td_launch_edge_mlp_tc(P, xm, src, etype, e->dist.as<float>(), row_nodes, n_rows, K, m, m.w2_img, e->mlp_mode, offsets, coeff, out, e->sm_count, st);
   else
     td_launch_edge_mlp(P, xm, src, etype, row_nodes, n_rows, K, m, offsets, coeff, out, e->sm_count, st);
@@ -621,13 +649,13 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
   else
     td_launch_knn(xm[0], e->node_ptr.as<int>(), e->B, e->max_ng, K, e->src.as<int>(), st);
   td_launch_edge_const(xm[0], src, e->src_prev.as<int>(), e->have_prev ? 1 : 0, N, K, e->ew_off, e->ew_coeff, e->ew_w1t, e->ew_b1, e->ew_g, e->ew_b, e->ew_w2, e->ew_b2,
-                       e->etype.as<unsigned char>(), e->e_w.as<float>(), e->slow_list.as<int>(), e->n_slow.as<int>(), e->rel_flag.as<unsigned char>(),
-                       e->work_list.as<int>(), e->n_work.as<int>(), st);
+                       e->etype.as<unsigned char>(), e->e_w.as<float>(), e->rel_flag.as<unsigned char>(), e->work_list.as<int>(), e->n_work.as<int>(), st);
   td_launch_rel_compact(e->rel_flag.as<unsigned char>(), N, e->rel_list.as<int>(), e->n_rel.as<int>(), st);
   e->launches += 5;
-  if (e->slow_tc) {
-    td_launch_slow_bucket(e->slow_list.as<int>(), e->n_slow.as<int>(), etype, e->type_list.as<int>(), (long long)N * K, e->n_type.as<int>(), e->sm_count, st);
-    e->launches += 1;
+  if (fused_logits(e) && e->restrict_last) {       // class-sorted list of the relevant destinations for the last layer's x2h
+    td_launch_rel_rows(e->rel_flag.as<unsigned char>(), xm[0], N, e->lig_rows.as<int>(), (int)e->lig_n_dst, e->row_pad, e->rel_rows.as<int>(),
+                       e->rel_counts.as<int>(), st);
+    e->launches += 2;
   }
   int cur = 0;
   for (size_t l = 0; l < e->layers.size(); ++l) {
@@ -640,21 +668,20 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     // sampling loop, last layer: only the ligand atoms' features feed the type head and only ligand atoms + their neighbours feed
     // the last h2x, so x2h is evaluated for those destinations only (device-compacted list; final_h of other nodes is not produced)
     const bool sub = fuse_agg && e->restrict_last && l + 1 == e->layers.size() && !e->env_no_restrict;
-    const int* rows = sub ? e->rel_list.as<int>() : nullptr;
-    const int* d_n = sub ? e->n_rel.as<int>() : nullptr;
+    const RowList rl = sub ? ROWS_RELEVANT : ROWS_ALL;
     {
       Prof pr(e, st, EV_EDGE_MLP);
-      edge_mlp(e, P, xm[cur], src, etype, rows, (long long)N * K, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st,
-               fused_logits(e) ? q : nullptr, nullptr, nullptr, 0, d_n, fuse_agg ? 1 : 0);
-      edge_mlp(e, P, xm[cur], src, etype, rows, (long long)N * K, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), st, nullptr,
-               fuse_agg ? e->kbuf.as<float>() : nullptr, fuse_agg ? h : nullptr, N, d_n);
+      edge_mlp(e, P, xm[cur], src, etype, rl, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st, fused_logits(e) ? q : nullptr, nullptr,
+               nullptr, fuse_agg ? 1 : 0);
+      edge_mlp(e, P, xm[cur], src, etype, rl, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), st, nullptr,
+               fuse_agg ? e->kbuf.as<float>() : nullptr, fuse_agg ? h : nullptr);
     }
     if (!fuse_agg) {
       Prof pr(e, st, EV_AGG_H);
       if (fused_logits(e)) td_launch_aggregate_h_logits(e->kbuf.as<float>(), e->vbuf.as<float>(), e->e_w.as<float>(), src, h, h, N, K, st);
       else td_launch_aggregate_h(e->kbuf.as<float>(), e->vbuf.as<float>(), e->e_w.as<float>(), src, q, h, h, N, K, st);
     }
-    e->launches += fuse_agg ? 6 : (fused_logits(e) ? 7 : 5);
+    e->launches += fuse_agg ? 4 : 5;
     if (fix_x || Nl == 0) continue;     // h2x only moves ligand atoms; with fix_x its result is discarded (:204-206)
     // ---- h2x: x_lig <- x_lig + mean_heads sum_e alpha * v * e_w * (x_dst - x_src), destinations = ligand atoms only
     {
@@ -663,9 +690,8 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
     }
     {
       Prof pr(e, st, EV_EDGE_MLP);
-      edge_mlp(e, P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st,
-               fused_logits(e) ? q : nullptr);
-      edge_mlp(e, P, xm[cur], src, etype, e->lig_node.as<int>(), (long long)Nl * K, K, ly.h2x.v, ly.offsets, ly.coeff, e->v16.as<float>(), st);
+      edge_mlp(e, P, xm[cur], src, etype, ROWS_LIGAND, K, ly.h2x.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st, fused_logits(e) ? q : nullptr);
+      edge_mlp(e, P, xm[cur], src, etype, ROWS_LIGAND, K, ly.h2x.v, ly.offsets, ly.coeff, e->v16.as<float>(), st);
     }
     {
       Prof pr(e, st, EV_AGG_X);
@@ -964,7 +990,7 @@ extern "C" int tdiff_scatter_mean3(const float* d_src, const int32_t* h_counts, 
 
 // ---------------------------------------------------------------------------------------------- instrumentation
 extern "C" int64_t tdiff_launch_count(tdiff_engine* e) { return e ? e->launches : 0; }
-extern "C" int tdiff_edge_mlp_mode(tdiff_engine* e) { return !e ? TDIFF_EINVAL : (e->mlp_mode == 2 && e->mlp_v3) ? 5 : e->mlp_mode; }
+extern "C" int tdiff_edge_mlp_mode(tdiff_engine* e) { return !e ? TDIFF_EINVAL : (e->mlp_mode == 2 && e->mlp_v4) ? 5 : e->mlp_mode; }
 
 extern "C" int tdiff_profile(tdiff_engine* e, int enable) {
   if (!e) return set_err(TDIFF_EINVAL, "null engine");

@@ -29,16 +29,8 @@ struct TdMlp {
   int nout;            // 128 or 16
   int offA, offB;      // column offsets into the node projection P
   const unsigned char* w2_img;   // nout==128 edge MLPs: second Linear as 3 bf16 pieces in the UMMA K-major SWIZZLE_128B image
-  const unsigned char* tab3_img; // type-3 (protein-protein) gaussian/type block [128 x 32] as bf16 pieces, K-major SWIZZLE_64B image
-  const unsigned char* tab012_img;   // same images for types 0, 1, 2 (3 x 24 KB), only packed with TDIFF_SLOW_TC=1, else NULL
-};
-
-// experimental tensor-core pre-pass for the rare edge types (edge_mlp_v3.cu, TDIFF_SLOW_TC=1)
-struct TdSlowTc {
-  const int* type_list;    // [3][cap] slots of type 0 / 1 / 2 (bucketed slow list)
-  long long cap;
-  const int* n_type;       // [3] device counts
-  const int* node_rank;    // node -> ligand rank (row = rank * k + j) for launches over the ligand destinations, else NULL
+  const unsigned char* tabcls_img;   // gaussian/type blocks per destination class: 2 x [128 x 64] in two bf16 pieces, K-major SWIZZLE_128B
+                                     // (class 0 = protein destination: types 3 | 1, class 1 = ligand destination: types 2 | 0)
 };
 
 struct TdSubLayer {       // x2h or h2x
@@ -138,8 +130,9 @@ void td_launch_knn_update(const float4* xm, const int* node_ptr, const int* prot
                           const unsigned long long* cache, int* src, cudaStream_t st);
 void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int have_prev, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
-                          unsigned char* etype, float* e_w, int* slow_list, int* n_slow, unsigned char* rel_flag, int* work_list, int* n_work,
-                          cudaStream_t st);
+                          unsigned char* etype, float* e_w, unsigned char* rel_flag, int* work_list, int* n_work, cudaStream_t st);
+void td_launch_rel_rows(const unsigned char* rel_flag, const float4* xm, int n_nodes, const int* lig_rows, int n_lig_rows, int pad, int* rel_rows,
+                        int* rel_counts, cudaStream_t st);
 void td_launch_protein_embed(const float* feat, int n_protein, int fdim, const float* w, const float* b, const int* prot_node,
                              float* h0, cudaStream_t st);
 void td_launch_init_h(const float* h0, const float4* xm, const int* lig_v, const int* node_lig, const float* wl_t, const float* bl,
@@ -152,13 +145,10 @@ void td_launch_edge_geom(const float4* xm, const int* src, int n_nodes, int k, f
 void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const float* dist,
                            const int* row_nodes, long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
                            float* out, int sm_count, cudaStream_t st);
-void td_launch_edge_mlp_v3(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_rows,
-                           int k, TdMlp m, const unsigned char* w2_image, const unsigned char* tab3_image, const float* offsets, float coeff,
-                           const float* h_ln_g, const float* h_ln_b, const float* h_b2, float* tslow, const int* slow_list, const int* n_slow,
-                           const float* qnode, float* out, const float* agg_logits, const float* agg_e_w, float* agg_h, int agg_n_nodes,
-                           const int* d_n_dst, int key_softmax, const TdSlowTc* stc, int sm_count, cudaStream_t st);
-void td_launch_slow_bucket(const int* slow_list, const int* n_slow, const unsigned char* etype, int* type_list, long long cap, int* n_type,
-                           int sm_count, cudaStream_t st);
+void td_launch_edge_mlp_v4(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_dst,
+                           long long split_dst, const int* d_counts, int k, const TdMlp& m, const float* offsets, float coeff,
+                           const float* h_ln_g, const float* h_ln_b, const float* h_b2, const float* qnode, float* out, int out_by_slot,
+                           const float* agg_logits, const float* agg_e_w, float* agg_h, int key_softmax, int sm_count, cudaStream_t st);
 void td_launch_rows_tc(int mode, const float* in, int ldi, int in_off, long long n_rows, TdMlp m, const unsigned char* w_image, int pieces, float* out,
                        int ldo, int nblocks, const int* row_list, const int* d_n_rows, int sm_count, cudaStream_t st);
 void td_launch_rel_compact(const unsigned char* flag, int n_nodes, int* rel_list, int* n_rel, cudaStream_t st);

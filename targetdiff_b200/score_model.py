@@ -262,9 +262,10 @@ class ScorePosNet3D(nn.Module):
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
     def forward(self, protein_pos, protein_v, batch_protein, init_ligand_pos, init_ligand_v, batch_ligand,
-                time_step=None, return_all=False, fix_x=False):
+                time_step=None, return_all=False, fix_x=False, return_edge_weight=False):
         """One network evaluation (reference models/molopt_score_model.py:313-368; time_emb_dim=0 so `time_step` is unused).
-        Returns {'pred_ligand_pos','pred_ligand_v','final_h','final_ligand_h'}; additionally 'edge_index' (int64 [2,E])."""
+        Returns {'pred_ligand_pos','pred_ligand_v','final_h','final_ligand_h'}; additionally 'edge_index' (int64 [2,E]) and, with
+        `return_edge_weight`, 'edge_weight' [E]: the global edge gate e_w in edge_index order (models/uni_transformer.py:312-316)."""
         if return_all:
             raise NotImplementedError('return_all=True (per-block outputs) is not implemented by the B200 engine')
         dev = protein_pos.device
@@ -288,8 +289,13 @@ class ScorePosNet3D(nn.Module):
         _lib.check(lib.tdiff_get_edge_index(eng, _ptr(edge_index), st))
         # ligand rows of the composed node order: per graph, protein atoms then ligand atoms
         lig_rows = self._ligand_rows(batch_protein, batch_ligand, B, dev)
-        return {'pred_ligand_pos': pred_pos, 'pred_ligand_v': logits, 'final_h': final_h, 'final_ligand_h': final_h[lig_rows],
-                'edge_index': edge_index}
+        out = {'pred_ligand_pos': pred_pos, 'pred_ligand_v': logits, 'final_h': final_h, 'final_ligand_h': final_h[lig_rows],
+               'edge_index': edge_index}
+        if return_edge_weight:
+            e_w = torch.empty(E, device=dev)
+            _lib.check(lib.tdiff_get_edge_weight(eng, _ptr(e_w), st))
+            out['edge_weight'] = e_w
+        return out
 
     @staticmethod
     def _ligand_rows(batch_protein, batch_ligand, B, dev):
@@ -331,8 +337,8 @@ class ScorePosNet3D(nn.Module):
             v_uniform = noise_tape[1].detach().to(dev, torch.float32).contiguous()
             if tuple(pos_noise.shape) != (S, Nl, 3) or tuple(v_uniform.shape) != (S, Nl, K):
                 raise ValueError('noise tape shapes must be [S,Nl,3] and [S,Nl,K]')
-        if seed is None:
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if seed is None:        # with a tape the Philox key is unused: do not advance the caller's CPU generator (rng='cpu' driver parity)
+            seed = 0 if noise_tape is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
         pos_traj = v_traj = v0_traj = vt_traj = None
         if return_traj:
             pos_traj = torch.empty(S, Nl, 3, device=dev)

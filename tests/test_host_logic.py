@@ -63,7 +63,7 @@ class _FakeModel:
         self.calls = []
 
     def sample_diffusion(self, protein_pos, protein_v, batch_protein, init_ligand_pos, init_ligand_v, batch_ligand, num_steps, pos_only,
-                         center_pos_mode, stack_traj):
+                         center_pos_mode, stack_traj, noise_tape=None):
         S, nl = num_steps, len(batch_ligand)
         self.calls.append((int(batch_protein.max()) + 1, nl))
         ar = torch.arange(nl, dtype=torch.float32)

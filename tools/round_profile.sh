@@ -1,0 +1,23 @@
+#!/bin/bash
+# Measurements of one build on one B200 (run through gpurun); everything lands in gpurun_out/<tag>_*.
+#   tools/round_profile.sh <tag> [tests|bench|full|ncu|audit ...]
+tag=${1:-r02}; shift
+what=${*:-tests bench ncu}
+mkdir -p gpurun_out
+for w in $what; do
+  case $w in
+    tests) timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; tail -3 gpurun_out/${tag}_pytest_gpu.log ;;
+    bench) timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 300 gpurun_out/${tag}_bench.err; cut -c1-330 gpurun_out/${tag}_bench.json ;;
+    reference) timeout 600 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${tag}_reference.json 2> gpurun_out/${tag}_reference.err; cut -c1-300 gpurun_out/${tag}_reference.json ;;
+    full) timeout 900 python bench.py --full-chain --no-cpu-baseline > gpurun_out/${tag}_bench_full_chain.json 2> gpurun_out/${tag}_bench_full_chain.err; cut -c1-330 gpurun_out/${tag}_bench_full_chain.json ;;
+    cfg2) timeout 600 python bench.py --workload cfg2 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_cfg2.json 2> gpurun_out/${tag}_bench_cfg2.err; cut -c1-330 gpurun_out/${tag}_bench_cfg2.json ;;
+    cfg5) timeout 600 python bench.py --workload cfg5 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_cfg5.json 2> gpurun_out/${tag}_bench_cfg5.err; cut -c1-330 gpurun_out/${tag}_bench_cfg5.json ;;
+    ncu)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv python tools/eager_steps.py 3 > gpurun_out/${tag}_launches.log 2>&1
+      python tools/launch_shares.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_launch_shares.csv; head -14 gpurun_out/${tag}_launch_shares.csv
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:edge_mlp_v4_kernel -s 6 -c 2 -o gpurun_out/${tag}_v4 python tools/eager_steps.py 2 > gpurun_out/${tag}_ncu.log 2>&1
+      ncu -i gpurun_out/${tag}_v4.ncu-rep --page raw --csv > gpurun_out/${tag}_v4_raw.csv 2>/dev/null
+      ncu -i gpurun_out/${tag}_v4.ncu-rep --page source --csv > gpurun_out/${tag}_v4_source.csv 2>/dev/null ;;
+    audit) timeout 900 python tools/precision_audit.py --out gpurun_out/${tag}_precision_audit.json > gpurun_out/${tag}_audit.log 2>&1; tail -8 gpurun_out/${tag}_audit.log ;;
+  esac
+done

@@ -53,7 +53,14 @@ typedef struct tdiff_config {
   int32_t num_timesteps;     /* num_diffusion_timesteps, 1000 */
   int32_t model_mean_type;   /* 0 = 'C0' (network predicts x0), 1 = 'noise' (x0 from the predicted displacement,
                               * reference models/molopt_score_model.py:419-422,663-666) */
-  int32_t reserved[7];       /* must be 0 */
+  int32_t num_blocks;        /* 0 or 1: one block; n > 1: the k-NN graph is rebuilt from the updated coordinates and the SAME layers run
+                              * again, n times in total (models/uni_transformer.py:306-321) */
+  int32_t ew_net_type;       /* edge gate: 0 'global' (one MLP gate per forward, :312-316), 1 'r' (per sub-layer Linear(r_feat) -> sigmoid,
+                              * :58-59,121-122), 2 'm' (x2h: Linear(value) -> sigmoid, h2x: 1, :60-61,123-124), 3 'none' (1) */
+  int32_t x2h_out_fc;        /* 1: node_output MLP on [aggregate | h] before the residual (:39-40,80-81) */
+  int32_t time_emb;          /* 0: time_emb_dim = 0; 1: time_emb_mode 'simple', one extra ligand input column time_step / T
+                              * (models/molopt_score_model.py:319-324); 'sin' cannot run in the reference itself (:325-326) */
+  int32_t reserved[3];       /* must be 0 */
 } tdiff_config;
 
 /* One state_dict entry (reference key name, fp32, host memory).  SURVEY.md Appendix D lists the 384 keys. */
@@ -87,6 +94,10 @@ TDIFF_API int tdiff_set_ligand(tdiff_engine* e, const float* d_ligand_pos, const
 TDIFF_API int tdiff_get_ligand(tdiff_engine* e, float* d_ligand_pos, int64_t* d_ligand_v, int add_offset, void* stream);
 /* Per-graph centring offset [n_graphs,3] (zeros for center_mode 0). */
 TDIFF_API int tdiff_get_offset(tdiff_engine* e, float* d_offset, void* stream);
+
+/* Time step of every graph for the next tdiff_forward, as time_step / num_timesteps (fp32, device, [n_graphs]); only read when the
+ * engine was created with time_emb = 1 (models/molopt_score_model.py:319-324).  tdiff_sample sets it itself every step. */
+TDIFF_API int tdiff_set_time(tdiff_engine* e, const float* d_time_norm, void* stream);
 
 /* ---- one network evaluation ----------------------------------------------------------------------------
  * Replaces: ScorePosNet3D.forward (models/molopt_score_model.py:313-368) for time_emb_dim=0 on the bound batch and

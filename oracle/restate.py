@@ -219,30 +219,46 @@ def scatter_sum_rows(src, index, n):
 # ----------------------------------------------------------------------------------------------
 # a10-a12  attention layers                                       models/uni_transformer.py:42-84,108-140,181-210
 # ----------------------------------------------------------------------------------------------
-def x2h_layer(sd, prefix, h, r_feat, edge_feat, edge_index, e_w, n_heads):
+def _edge_weight(sd, prefix, ew_net_type, r_feat, v, e_w):
+    """The per-edge gate of one attention sub-layer (uni_transformer.py:58-66 / :121-129)."""
+    if ew_net_type == 'r':
+        return torch.sigmoid(F.linear(r_feat, sd[prefix + '.ew_net.0.weight'], sd[prefix + '.ew_net.0.bias']))     # :58-59,121-122
+    if ew_net_type == 'm':
+        if v is None:
+            return 1.                                                                                           # h2x: :123-124
+        H = sd[prefix + '.ew_net.0.weight'].shape[1]
+        return torch.sigmoid(F.linear(v[..., :H], sd[prefix + '.ew_net.0.weight'], sd[prefix + '.ew_net.0.bias']))  # :60-61
+    if e_w is not None:
+        return e_w.view(-1, 1)                                                                                  # :62-63
+    return 1.                                                                                                   # :64-65
+
+
+def x2h_layer(sd, prefix, h, r_feat, edge_feat, edge_index, e_w, n_heads, ew_net_type='global', out_fc=False):
     N = h.size(0)
     src, dst = edge_index
     kv_input = torch.cat([edge_feat, torch.cat([r_feat, h[dst], h[src]], -1)], -1)       # :45-51
     H = h.shape[1]
     k = mlp(sd, prefix + '.hk_func', kv_input).view(-1, n_heads, H // n_heads)           # :54
     v = mlp(sd, prefix + '.hv_func', kv_input)                                           # :56
-    v = v * e_w.view(-1, 1)                                                              # :62-66
+    v = v * _edge_weight(sd, prefix, ew_net_type, r_feat, v, e_w)                        # :58-66
     v = v.view(-1, n_heads, H // n_heads)
     q = mlp(sd, prefix + '.hq_func', h).view(-1, n_heads, H // n_heads)                  # :70
     alpha = scatter_softmax_rows((q[dst] * k / np.sqrt(k.shape[-1])).sum(-1), dst, N)    # :73-74
     m = alpha.unsqueeze(-1) * v                                                          # :77
     out = scatter_sum_rows(m, dst, N).view(-1, H)                                        # :78-79
-    return out + h                                                                       # :83 (out_fc=False)
+    if out_fc:
+        out = mlp(sd, prefix + '.node_output', torch.cat([out, h], -1))                  # :80-81
+    return out + h                                                                       # :83
 
 
-def h2x_layer(sd, prefix, h, rel_x, r_feat, edge_feat, edge_index, e_w, n_heads):
+def h2x_layer(sd, prefix, h, rel_x, r_feat, edge_feat, edge_index, e_w, n_heads, ew_net_type='global'):
     N = h.size(0)
     src, dst = edge_index
     kv_input = torch.cat([edge_feat, torch.cat([r_feat, h[dst], h[src]], -1)], -1)       # :111-117
     H = h.shape[1]
     k = mlp(sd, prefix + '.xk_func', kv_input).view(-1, n_heads, H // n_heads)           # :119
     v = mlp(sd, prefix + '.xv_func', kv_input)                                           # :120
-    v = v * e_w.view(-1, 1)                                                              # :125-129
+    v = v * _edge_weight(sd, prefix, ew_net_type, r_feat, None, e_w)                     # :121-129
     v = v.unsqueeze(-1) * rel_x.unsqueeze(1)                                             # :131
     q = mlp(sd, prefix + '.xq_func', h).view(-1, n_heads, H // n_heads)                  # :132
     alpha = scatter_softmax_rows((q[dst] * k / np.sqrt(k.shape[-1])).sum(-1), dst, N)    # :135
@@ -250,39 +266,45 @@ def h2x_layer(sd, prefix, h, rel_x, r_feat, edge_feat, edge_index, e_w, n_heads)
     return scatter_sum_rows(m, dst, N).mean(1)                                           # :139-140
 
 
-def att_layer(sd, prefix, h, x, edge_type, edge_index, mask_ligand, e_w, n_heads, fix_x=False):
+def att_layer(sd, prefix, h, x, edge_type, edge_index, mask_ligand, e_w, n_heads, fix_x=False, ew_net_type='global', out_fc=False):
     """AttentionLayerO2TwoUpdateNodeGeneral.forward, num_x2h=num_h2x=1, sync_twoup=False (:181-210)."""
     src, dst = edge_index
     offset = sd[prefix + '.distance_expansion.offset']
     rel_x = x[dst] - x[src]                                                              # :188
     dist = torch.norm(rel_x, p=2, dim=-1, keepdim=True)                                  # :189
     r_feat = outer_product_type_gauss(edge_type, gaussian_smearing(dist, offset))        # :194-195
-    h_out = x2h_layer(sd, prefix + '.x2h_layers.0', h, r_feat, edge_type, edge_index, e_w, n_heads)
+    h_out = x2h_layer(sd, prefix + '.x2h_layers.0', h, r_feat, edge_type, edge_index, e_w, n_heads, ew_net_type, out_fc)
     r_feat = outer_product_type_gauss(edge_type, gaussian_smearing(dist, offset))        # :202-203
-    dx = h2x_layer(sd, prefix + '.h2x_layers.0', h_out, rel_x, r_feat, edge_type, edge_index, e_w, n_heads)
+    dx = h2x_layer(sd, prefix + '.h2x_layers.0', h_out, rel_x, r_feat, edge_type, edge_index, e_w, n_heads, ew_net_type)
     if not fix_x:
         x = x + dx * mask_ligand[:, None]                                                # :205-206
     return h_out, x
 
 
 def refine_net(sd, cfg, h, x, mask_ligand, batch, fix_x=False, edge_index=None, trace=None):
-    """UniTransformerO2TwoUpdateGeneral.forward (uni_transformer.py:301-328), num_blocks=1, knn, ew 'global'."""
-    assert cfg['num_blocks'] == 1 and cfg['cutoff_mode'] == 'knn' and cfg['ew_net_type'] == 'global'
-    if edge_index is None:
-        edge_index = knn_graph_canonical(x, cfg['knn'], batch)                           # :307
-    src, dst = edge_index
-    edge_type = build_edge_type(edge_index, mask_ligand)                                 # :311
-    dist = torch.norm(x[dst] - x[src], p=2, dim=-1, keepdim=True)                        # :313
-    dist_feat = gaussian_smearing(dist, sd['refine_net.distance_expansion.offset'])      # :314
-    e_w = torch.sigmoid(mlp(sd, 'refine_net.edge_pred_layer', dist_feat))                # :315-316
-    if trace is not None:
-        trace.update(edge_index=edge_index, edge_type=edge_type.argmax(-1), e_w=e_w.view(-1), all_h=[h], all_x=[x])
-    for l in range(cfg['num_layers']):
-        h, x = att_layer(sd, 'refine_net.base_block.%d' % l, h, x, edge_type, edge_index, mask_ligand, e_w,
-                         cfg['n_heads'], fix_x=fix_x)                                    # :320-321
+    """UniTransformerO2TwoUpdateGeneral.forward (uni_transformer.py:301-328): num_blocks x (k-NN graph, edge types, optional global
+    gate, the SAME num_layers attention layers)."""
+    assert cfg['cutoff_mode'] == 'knn' and cfg['ew_net_type'] in ('global', 'r', 'm', 'none')
+    given = edge_index
+    for b in range(cfg['num_blocks']):                                                   # :306
+        edge_index = given if (given is not None and b == 0) else knn_graph_canonical(x, cfg['knn'], batch)   # :307
+        src, dst = edge_index
+        edge_type = build_edge_type(edge_index, mask_ligand)                             # :311
+        e_w = None
+        if cfg['ew_net_type'] == 'global':                                               # :312-318
+            dist = torch.norm(x[dst] - x[src], p=2, dim=-1, keepdim=True)
+            dist_feat = gaussian_smearing(dist, sd['refine_net.distance_expansion.offset'])
+            e_w = torch.sigmoid(mlp(sd, 'refine_net.edge_pred_layer', dist_feat))
+        if trace is not None and b == 0:
+            trace.update(edge_index=edge_index, edge_type=edge_type.argmax(-1), e_w=None if e_w is None else e_w.view(-1), all_h=[h], all_x=[x])
+        for l in range(cfg['num_layers']):
+            h, x = att_layer(sd, 'refine_net.base_block.%d' % l, h, x, edge_type, edge_index, mask_ligand, e_w,
+                             cfg['n_heads'], fix_x=fix_x, ew_net_type=cfg['ew_net_type'], out_fc=cfg['x2h_out_fc'])   # :320-321
+            if trace is not None and b == 0:
+                trace['all_h'].append(h)
+                trace['all_x'].append(x)
         if trace is not None:
-            trace['all_h'].append(h)
-            trace['all_x'].append(x)
+            trace.setdefault('block_edge_index', []).append(edge_index)
     return {'x': x, 'h': h}
 
 
@@ -298,12 +320,16 @@ def compose_context(h_protein, h_ligand, pos_protein, pos_ligand, batch_protein,
 
 
 def forward(sd, cfg, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v, batch_ligand,
-            fix_x=False, trace=None):
-    """ScorePosNet3D.forward with time_emb_dim=0, node_indicator=True (molopt_score_model.py:313-368)."""
+            fix_x=False, trace=None, time_step=None):
+    """ScorePosNet3D.forward, node_indicator=True (molopt_score_model.py:313-368); time_emb_dim = 0 or time_emb_mode 'simple'
+    ('sin' cannot run in the reference: `time_feat` is [B, dim] but is concatenated with the [Nl, K] one-hot, :325-326)."""
     cfg = dict(DEFAULT_MODEL_CONFIG, **(cfg or {}))
-    assert cfg['time_emb_dim'] == 0 and cfg['node_indicator']
-    K = sd['ligand_atom_emb.weight'].shape[1]
+    assert cfg['node_indicator'] and (cfg['time_emb_dim'] == 0 or cfg['time_emb_mode'] == 'simple')
+    T = sd['betas'].shape[0]
+    K = sd['ligand_atom_emb.weight'].shape[1] - (1 if cfg['time_emb_dim'] > 0 else 0)
     lig_feat = F.one_hot(ligand_v, K).float()                                            # :317
+    if cfg['time_emb_dim'] > 0:                                                          # :319-324
+        lig_feat = torch.cat([lig_feat, (time_step / T)[batch_ligand].unsqueeze(-1)], -1)
     h_p = F.linear(protein_v, sd['protein_atom_emb.weight'], sd['protein_atom_emb.bias'])  # :333
     h_l = F.linear(lig_feat, sd['ligand_atom_emb.weight'], sd['ligand_atom_emb.bias'])     # :334
     h_p = torch.cat([h_p, torch.zeros(len(h_p), 1)], -1)                                 # :336-338
@@ -331,7 +357,7 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
     cfg = dict(DEFAULT_MODEL_CONFIG, **(cfg or {}))
     assert cfg['model_mean_type'] in ('C0', 'noise')
     T = sd['betas'].shape[0]
-    K = sd['ligand_atom_emb.weight'].shape[1]
+    K = sd['v_inference.2.weight'].shape[0]
     if num_steps is None:
         num_steps = T
     num_graphs = int(batch_protein.max()) + 1
@@ -345,7 +371,7 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
     time_seq = list(reversed(range(T - num_steps, T)))                                   # :649
     for s, i in enumerate(time_seq):
         t = torch.full((num_graphs,), i, dtype=torch.long)                               # :651
-        preds = forward(sd, cfg, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v, batch_ligand)
+        preds = forward(sd, cfg, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v, batch_ligand, time_step=t)
         pos0, v0 = preds['pred_ligand_pos'], preds['pred_ligand_v']                      # :667-669
         if cfg['model_mean_type'] == 'noise':                                            # :663-666 with :419-422
             eps = pos0 - ligand_pos

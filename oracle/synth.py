@@ -44,15 +44,25 @@ def _mlp_spec(prefix, in_dim, out_dim, hidden):
 
 
 def _att_layer_spec(prefix, cfg, num_x2h, num_h2x):
+    """reference models/uni_transformer.py:11-40,86-106,143-179 (module order = state_dict order)"""
     H, nh, ng = cfg['hidden_dim'], cfg['n_heads'], cfg['num_r_gaussian']
-    kv_in = 2 * H + cfg['edge_feat_dim'] + 4 * ng
+    r_dim = 4 * ng
+    kv_in = 2 * H + cfg['edge_feat_dim'] + r_dim
+    ew = cfg['ew_net_type']
     spec = [(prefix + '.distance_expansion.offset', (20,), 'offset')]
     for i in range(num_x2h):
         p = '%s.x2h_layers.%d' % (prefix, i)
         spec += _mlp_spec(p + '.hk_func', kv_in, H, H) + _mlp_spec(p + '.hv_func', kv_in, H, H) + _mlp_spec(p + '.hq_func', H, H, H)
+        if ew in ('r', 'm'):
+            d = r_dim if ew == 'r' else H
+            spec += [(p + '.ew_net.0.weight', (1, d), 'lin_w'), (p + '.ew_net.0.bias', (1,), 'lin_b:%d' % d)]
+        if cfg['x2h_out_fc']:
+            spec += _mlp_spec(p + '.node_output', 2 * H, H, H)
     for i in range(num_h2x):
         p = '%s.h2x_layers.%d' % (prefix, i)
         spec += _mlp_spec(p + '.xk_func', kv_in, H, H) + _mlp_spec(p + '.xv_func', kv_in, nh, H) + _mlp_spec(p + '.xq_func', H, H, H)
+        if ew == 'r':
+            spec += [(p + '.ew_net.0.weight', (1, r_dim), 'lin_w'), (p + '.ew_net.0.bias', (1,), 'lin_b:%d' % r_dim)]
     return spec
 
 
@@ -64,7 +74,8 @@ def state_dict_spec(cfg=None, protein_dim=PROTEIN_FEATURE_DIM, ligand_dim=LIGAND
     spec = [(k, (T,), 'schedule') for k in SCHEDULE_KEYS]
     spec += [('Lt_history', (T,), 'zeros'), ('Lt_count', (T,), 'zeros')]
     spec += [('protein_atom_emb.weight', (emb, protein_dim), 'lin_w'), ('protein_atom_emb.bias', (emb,), 'lin_b:%d' % protein_dim)]
-    spec += [('ligand_atom_emb.weight', (emb, ligand_dim), 'lin_w'), ('ligand_atom_emb.bias', (emb,), 'lin_b:%d' % ligand_dim)]
+    lig_in = ligand_dim + (0 if cfg['time_emb_dim'] == 0 else 1 if cfg['time_emb_mode'] == 'simple' else cfg['time_emb_dim'])
+    spec += [('ligand_atom_emb.weight', (emb, lig_in), 'lin_w'), ('ligand_atom_emb.bias', (emb,), 'lin_b:%d' % lig_in)]
     spec += [('refine_net.distance_expansion.offset', (20,), 'offset')]
     if cfg['ew_net_type'] == 'global':
         spec += _mlp_spec('refine_net.edge_pred_layer', cfg['num_r_gaussian'], 1, H)

@@ -20,7 +20,8 @@ class TdiffError(RuntimeError):
 class tdiff_config(ctypes.Structure):
     _fields_ = [('hidden_dim', ctypes.c_int32), ('n_heads', ctypes.c_int32), ('num_layers', ctypes.c_int32), ('knn', ctypes.c_int32),
                 ('num_r_gaussian', ctypes.c_int32), ('num_classes', ctypes.c_int32), ('protein_feat_dim', ctypes.c_int32),
-                ('num_timesteps', ctypes.c_int32), ('model_mean_type', ctypes.c_int32), ('reserved', ctypes.c_int32 * 7)]
+                ('num_timesteps', ctypes.c_int32), ('model_mean_type', ctypes.c_int32), ('num_blocks', ctypes.c_int32),
+                ('ew_net_type', ctypes.c_int32), ('x2h_out_fc', ctypes.c_int32), ('time_emb', ctypes.c_int32), ('reserved', ctypes.c_int32 * 3)]
 
 
 class tdiff_tensor(ctypes.Structure):
@@ -40,6 +41,7 @@ SIGNATURES = {
     'tdiff_set_ligand': (_i, [_vp, _vp, _vp, _i, _vp]),
     'tdiff_get_ligand': (_i, [_vp, _vp, _vp, _i, _vp]),
     'tdiff_get_offset': (_i, [_vp, _vp, _vp]),
+    'tdiff_set_time': (_i, [_vp, _vp, _vp]),
     'tdiff_forward': (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     'tdiff_num_edges': (_i64, [_vp, _vp]),
     'tdiff_get_edge_index': (_i, [_vp, _vp, _vp]),

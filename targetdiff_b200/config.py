@@ -48,15 +48,28 @@ def default_sampling_config():
 
 # Values the sm_100a engine implements; anything else is rejected loudly (SURVEY.md 8(b) "should-reject-clearly").
 _SUPPORTED = dict(model_mean_type=('C0', 'noise'), beta_schedule=('sigmoid', 'linear', 'quad', 'const', 'jsd', 'cosine'),
-                  v_beta_schedule=('cosine',), time_emb_dim=(0,), node_indicator=(True,), model_type=('uni_o2',),
-                  num_blocks=(1,), hidden_dim=(128,), n_heads=(16,), edge_feat_dim=(4,), num_r_gaussian=(20,), act_fn=('relu',),
-                  norm=(True,), cutoff_mode=('knn',), ew_net_type=('global',), num_x2h=(1,), num_h2x=(1,), x2h_out_fc=(False,),
-                  sync_twoup=(False,))
+                  v_beta_schedule=('cosine',), node_indicator=(True,), model_type=('uni_o2',),
+                  hidden_dim=(128,), n_heads=(16,), edge_feat_dim=(4,), num_r_gaussian=(20,), act_fn=('relu',),
+                  norm=(True,), cutoff_mode=('knn',), ew_net_type=('global', 'r', 'm', 'none'), num_x2h=(1,), num_h2x=(1,),
+                  x2h_out_fc=(False, True), sync_twoup=(False,))
+_WHY_NOT = {
+    'cutoff_mode': "'radius' crashes in the reference itself (models/uni_transformer.py:278 reads an undefined self.r); 'hybrid' gives ligand "
+                   "atoms n_ligand - 1 + k neighbours (models/common.py:165-212), beyond the engine's fixed-degree (<= 64) neighbour slots",
+    'model_type': "the EGNN backbone is outside the sampling path of the default model (SURVEY.md section 2)",
+}
 
 
 def check_supported(cfg):
     for k, allowed in _SUPPORTED.items():
         if k in cfg and cfg[k] not in allowed:
-            raise NotImplementedError('config %s=%r is not implemented by the B200 engine (supported: %s)' % (k, cfg[k], list(allowed)))
+            raise NotImplementedError('config %s=%r is not implemented by the B200 engine (supported: %s)%s' % (
+                k, cfg[k], list(allowed), '; ' + _WHY_NOT[k] if k in _WHY_NOT else ''))
     if not (1 <= int(cfg.knn) <= 64):
         raise NotImplementedError('knn=%r outside 1..64' % (cfg.knn,))
+    if not (1 <= int(cfg.get('num_blocks', 1)) <= 16):
+        raise NotImplementedError('num_blocks=%r outside 1..16' % (cfg.num_blocks,))
+    if int(cfg.get('time_emb_dim', 0)) > 0 and cfg.get('time_emb_mode', 'simple') != 'simple':
+        # 'sin' cannot run in the reference either: `time_feat` is [B, dim] but is concatenated with the [Nl, K] one-hot
+        # (models/molopt_score_model.py:325-326)
+        raise NotImplementedError("time_emb_mode=%r: only 'simple' is implemented (the reference's 'sin' branch fails on a shape mismatch)"
+                                  % (cfg.time_emb_mode,))

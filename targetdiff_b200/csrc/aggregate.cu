@@ -157,7 +157,8 @@ void td_launch_aggregate_x(const float* kbuf, const float* v16, const float* e_w
 // ------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(AGG_WARPS * 32)
 aggregate_h_logits_kernel(const float* __restrict__ logits, const float* __restrict__ vbuf, const float* __restrict__ e_w,
-                          const int* __restrict__ src, const float* __restrict__ h_in, float* __restrict__ h_out, int n_nodes, int k) {
+                          const int* __restrict__ src, const float* __restrict__ h_in, float* __restrict__ h_out, int n_nodes, int k,
+                          const float* __restrict__ ewm_w, float ewm_b) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
   if (n >= n_nodes) return;
@@ -166,6 +167,9 @@ aggregate_h_logits_kernel(const float* __restrict__ logits, const float* __restr
   for (int j = lane; j < k; j += 32) deg += (src[e0 + j] >= 0);
   deg = __reduce_add_sync(0xffffffffu, deg);
   const float4 hin = *reinterpret_cast<const float4*>(h_in + (size_t)n * TD_H + 4 * lane);
+  // ew_net_type 'm' (reference models/uni_transformer.py:60-61): the gate is sigmoid(Linear(value row)), evaluated on the fly
+  float4 wm = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ewm_w) wm = *reinterpret_cast<const float4*>(ewm_w + 4 * lane);
   float m = -INFINITY, l = 0.0f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int j0 = 0; j0 < deg; j0 += AGG_CH) {
@@ -177,6 +181,15 @@ aggregate_h_logits_kernel(const float* __restrict__ logits, const float* __restr
         vr[c] = ldg_stream4(vbuf + (e0 + j0 + c) * TD_H + 4 * lane);
         sg[c] = logits[(e0 + j0 + c) * TD_HEADS + (lane >> 1)];
         ew[c] = e_w[e0 + j0 + c];
+      }
+    }
+    if (ewm_w) {
+#pragma unroll
+      for (int c = 0; c < AGG_CH; ++c) {
+        if (j0 + c < deg) {          // warp-uniform
+          const float dot = warp_sum((vr[c].x * wm.x + vr[c].y * wm.y) + (vr[c].z * wm.z + vr[c].w * wm.w));
+          ew[c] = 1.0f / (1.0f + expf(-(dot + ewm_b)));
+        }
       }
     }
 #pragma unroll
@@ -204,9 +217,10 @@ aggregate_h_logits_kernel(const float* __restrict__ logits, const float* __restr
 }
 
 void td_launch_aggregate_h_logits(const float* logits, const float* vbuf, const float* e_w, const int* src, const float* h_in, float* h_out,
-                                  int n_nodes, int k, cudaStream_t st) {
+                                  int n_nodes, int k, const float* ewm_w, float ewm_b, cudaStream_t st) {
   if (n_nodes == 0) return;
-  aggregate_h_logits_kernel<<<(n_nodes + AGG_WARPS - 1) / AGG_WARPS, AGG_WARPS * 32, 0, st>>>(logits, vbuf, e_w, src, h_in, h_out, n_nodes, k);
+  aggregate_h_logits_kernel<<<(n_nodes + AGG_WARPS - 1) / AGG_WARPS, AGG_WARPS * 32, 0, st>>>(logits, vbuf, e_w, src, h_in, h_out, n_nodes, k,
+                                                                                             ewm_w, ewm_b);
 }
 
 __global__ void __launch_bounds__(AGG_WARPS * 32)

@@ -15,7 +15,7 @@
 // load-balanced over the whole GPU instead of sitting in the few warps that happen to own ligand neighbourhoods.
 __global__ void __launch_bounds__(EC_WARPS * 32)
 edge_touch_kernel(const float4* __restrict__ xm, const int* __restrict__ src, int* __restrict__ src_prev, int have_prev, int n_nodes, int k,
-                  unsigned char* __restrict__ rel_flag, int* __restrict__ work_list, int* __restrict__ n_work) {
+                  unsigned char* __restrict__ rel_flag, unsigned char* __restrict__ touch_flag, int* __restrict__ work_list, int* __restrict__ n_work) {
   const int lane = threadIdx.x & 31;
   const int warp0 = blockIdx.x * EC_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * EC_WARPS;
   for (int node = warp0; node < n_nodes; node += nwarps) {
@@ -35,6 +35,9 @@ edge_touch_kernel(const float4* __restrict__ xm, const int* __restrict__ src, in
     if (rel_flag && xd.w != 0.0f && lane == 0) rel_flag[node] = 1;
     same = __all_sync(0xffffffffu, same);
     touch = __any_sync(0xffffffffu, touch);
+    // "touched" = ligand atom or node with a ligand atom among its neighbours: the nodes whose features after the first x2h differ
+    // from their ligand-free values (engine.cu, ligand-free cache)
+    if (touch_flag && lane == 0) touch_flag[node] = touch ? 1 : 0;
     if (same && !touch) continue;
     if (lane == 0) work_list[atomicAdd(n_work, 1)] = node;
   }
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(EC_WARPS * 32)
 edge_gate_kernel(const float4* __restrict__ xm, const int* __restrict__ src, const int* __restrict__ work_list, const int* __restrict__ n_work,
                  int k, const float* __restrict__ offsets, float coeff, const float* __restrict__ w1t, const float* __restrict__ b1,
                  const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ w2, float b2,
-                 unsigned char* __restrict__ etype, float* __restrict__ e_w) {
+                 unsigned char* __restrict__ etype, float* __restrict__ e_w, int gate_mode) {
   __shared__ float s_w1t[TD_NG * TD_H];
   __shared__ float s_b1[TD_H], s_g[TD_H], s_b[TD_H], s_w2[TD_H];
   for (int i = threadIdx.x; i < TD_NG * TD_H; i += blockDim.x) s_w1t[i] = w1t[i];
@@ -66,6 +69,14 @@ edge_gate_kernel(const float4* __restrict__ xm, const int* __restrict__ src, con
       continue;
     }
     const float4 xd = xm[node], xs = xm[s];
+    if (gate_mode != 0) {            // ew_net_type 'r' / 'm' / 'none': no global gate, only the edge type (the slot's gate defaults to 1)
+      if (lane == 0) {
+        const bool ns = xs.w != 0.0f, nd = xd.w != 0.0f;
+        etype[e] = (unsigned char)(ns ? (nd ? 0 : 1) : (nd ? 2 : 3));
+        e_w[e] = 1.0f;
+      }
+      continue;
+    }
     const float dx = xd.x - xs.x, dy = xd.y - xs.y, dz = xd.z - xs.z;
     const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
     const float t = dist - mu;
@@ -93,19 +104,23 @@ edge_gate_kernel(const float4* __restrict__ xm, const int* __restrict__ src, con
 
 void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int have_prev, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
-                          unsigned char* etype, float* e_w, unsigned char* rel_flag, int* work_list, int* n_work, cudaStream_t st) {
+                          unsigned char* etype, float* e_w, unsigned char* rel_flag, unsigned char* touch_flag, int* work_list, int* n_work,
+                          int gate_mode, cudaStream_t st) {
   if (n_nodes == 0) return;
   int blocks = (n_nodes + EC_WARPS - 1) / EC_WARPS;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (rel_flag) cudaMemsetAsync(rel_flag, 0, (size_t)n_nodes, st);
   cudaMemsetAsync(n_work, 0, sizeof(int), st);
-  edge_touch_kernel<<<blocks, EC_WARPS * 32, 0, st>>>(xm, src, src_prev, have_prev, n_nodes, k, rel_flag, work_list, n_work);
-  edge_gate_kernel<<<148 * 8, EC_WARPS * 32, 0, st>>>(xm, src, work_list, n_work, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2, etype, e_w);
+  edge_touch_kernel<<<blocks, EC_WARPS * 32, 0, st>>>(xm, src, src_prev, have_prev, n_nodes, k, rel_flag, touch_flag, work_list, n_work);
+  edge_gate_kernel<<<148 * 8, EC_WARPS * 32, 0, st>>>(xm, src, work_list, n_work, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2, etype, e_w, gate_mode);
 }
 
 // Per-layer edge length |x_dst - x_src| (reference models/uni_transformer.py:188-189) for every slot, from the layer's input
 // coordinates; consumed by the tensor-core edge-MLP producers so that their metadata loads are plain coalesced streams.
-__global__ void edge_geom_kernel(const float4* __restrict__ xm, const int* __restrict__ src, long long n_slots, int k, float* __restrict__ dist) {
+// ew_net_type 'r' (:58-59,121-122): the two sub-layers' gates sigmoid(Linear(r_feat)) are evaluated here too -- r_feat is the
+// (edge type one-hot) x (20 gaussians) outer product, so Linear(r_feat) = b + sum_j w[20 type + j] g_j(dist).
+__global__ void edge_geom_kernel(const float4* __restrict__ xm, const int* __restrict__ src, const unsigned char* __restrict__ etype, long long n_slots,
+                                 int k, float* __restrict__ dist, TdEwR ew) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_slots) return;
   const int s = src[e];
@@ -116,11 +131,26 @@ __global__ void edge_geom_kernel(const float4* __restrict__ xm, const int* __res
     d = sqrtf(dx * dx + dy * dy + dz * dz);
   }
   dist[e] = d;
+  if (ew.w_x2h) {
+    float ax = ew.b_x2h, ah = ew.b_h2x;
+    if (s >= 0) {
+      const int ty = etype[e];
+#pragma unroll 4
+      for (int j = 0; j < TD_NG; ++j) {
+        const float t = d - ew.offsets[j];
+        const float g = expf(ew.coeff * (t * t));
+        ax = fmaf(g, ew.w_x2h[ty * TD_NG + j], ax);
+        ah = fmaf(g, ew.w_h2x[ty * TD_NG + j], ah);
+      }
+    }
+    ew.out_x2h[e] = s >= 0 ? 1.0f / (1.0f + expf(-ax)) : 0.0f;
+    ew.out_h2x[e] = s >= 0 ? 1.0f / (1.0f + expf(-ah)) : 0.0f;
+  }
 }
 
-void td_launch_edge_geom(const float4* xm, const int* src, int n_nodes, int k, float* dist, cudaStream_t st) {
+void td_launch_edge_geom(const float4* xm, const int* src, const unsigned char* etype, int n_nodes, int k, float* dist, const TdEwR& ew, cudaStream_t st) {
   const long long n = (long long)n_nodes * k;
-  if (n > 0) edge_geom_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(xm, src, n, k, dist);
+  if (n > 0) edge_geom_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(xm, src, etype, n, k, dist, ew);
 }
 
 // Compact the relevant-node flags into a list (order irrelevant: every row is processed independently); consumers bound by *n_rel.
@@ -154,4 +184,33 @@ void td_launch_rel_rows(const unsigned char* rel_flag, const float4* xm, int n_n
   if (n_nodes > 0) rel_rows_protein_kernel<<<(n_nodes + 255) / 256, 256, 0, st>>>(rel_flag, xm, n_nodes, rel_rows, rel_counts);
   const int n = n_lig_rows > pad ? n_lig_rows : pad;
   rel_rows_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(lig_rows, n_lig_rows, pad, rel_rows, rel_counts);
+}
+
+// ---- ligand-free cache support (engine.cu): a node's features after x2h layer l equal their ligand-free values unless the node is
+// "dirty": dirty_{l+1} = dirty_l  or  any neighbour in dirty_l   (dirty_1 = touched nodes, see edge_touch_kernel)
+__global__ void dirty_propagate_kernel(const unsigned char* __restrict__ in, const int* __restrict__ src, int n_nodes, int k, unsigned char* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (node >= n_nodes) return;
+  bool d = in[node] != 0;
+  for (int j = lane; j < k && !d; j += 32) {
+    const int s = src[(size_t)node * k + j];
+    if (s >= 0 && in[s]) d = true;
+  }
+  d = __any_sync(0xffffffffu, d);
+  if (lane == 0) out[node] = d ? 1 : 0;
+}
+void td_launch_dirty_propagate(const unsigned char* in, const int* src, int n_nodes, int k, unsigned char* out, cudaStream_t st) {
+  if (n_nodes > 0) dirty_propagate_kernel<<<(n_nodes + 7) / 8, 256, 0, st>>>(in, src, n_nodes, k, out);
+}
+// clean protein nodes take their cached ligand-free features (one warp per node, 512 B rows)
+__global__ void restore_clean_kernel(const unsigned char* __restrict__ dirty, const float4* __restrict__ xm, const float* __restrict__ h_free, int n_nodes,
+                                     float* __restrict__ h) {
+  const int lane = threadIdx.x & 31;
+  const int node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (node >= n_nodes || dirty[node] || xm[node].w != 0.0f) return;
+  reinterpret_cast<float4*>(h + (size_t)node * TD_H)[lane] = reinterpret_cast<const float4*>(h_free + (size_t)node * TD_H)[lane];
+}
+void td_launch_restore_clean(const unsigned char* dirty, const float4* xm, const float* h_free, int n_nodes, float* h, cudaStream_t st) {
+  if (n_nodes > 0) restore_clean_kernel<<<(n_nodes + 7) / 8, 256, 0, st>>>(dirty, xm, h_free, n_nodes, h);
 }

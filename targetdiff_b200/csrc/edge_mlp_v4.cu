@@ -20,9 +20,11 @@
 //
 // CTA = 28 warps, one CTA per SM, persistent over tiles of 128 edge rows:
 //   warps  0-7   epilogue      TMEM D -> +b2 -> logits / softmax weights / fused attention aggregation / plain rows   (72 regs)
-//   warps  8-11  gather        32 rows each: cp.async 512 B rows of P[src] -> S; warp 11 also issues the MMAs          (40)
+//   warps  8-11  gather        32 rows each: cp.async 512 B rows of P[src] -> S, the tile's few P[dst] rows -> D; warp 11 also
+//                              issues the MMAs                                                                        (40)
 //   warps 12-27  row threads   warp 12+q+4*qq: rows 32q..32q+31, feature quarter qq                                   (80)
-// Shared memory (197 KB): W2 pieces 64 KB | S fp32 72 KB (row stride 144 B) | G pieces 32 KB | class table pieces 32 KB | 4 KB exchange.
+// Shared memory (208 KB): W2 pieces 64 KB | S fp32 72 KB (row stride 144 B) | G pieces 32 KB | class table pieces 32 KB | 4 KB exchange
+//                         | 4 KB destination rows.
 // TMEM 512 columns: D[2] at 0/128, Dpre at 256, A pieces at 384 / 448.  bf16 split: 2 pieces / 3 products (a1b1 + a1b2 + a2b1).
 #include <stdio.h>
 #include <stdlib.h>
@@ -39,8 +41,9 @@ constexpr int kSRow = 144;                 // staging row stride (128 B of data 
 constexpr int kSAtom = 128 * kSRow;        // one feature quarter of the staging tile
 constexpr int kTabClassBytes = 2 * kAtom;  // one class table: 2 bf16 pieces of [128 x 64]
 // shared-memory map (bytes from the 1024-aligned base)
-constexpr int oW = 0, oG = oW + 4 * kAtom, oT = oG + 2 * kAtom, oS = oT + 2 * kAtom, oX = oS + 4 * kSAtom, oBar = oX + 2 * 2048,
-              kSmem = oBar + 16 * 8 + 16;
+constexpr int kDstSlots = 8;               // destination rows P[dst, offA:+128] staged per tile (a tile spans <= 128/k + 2 destinations)
+constexpr int oW = 0, oG = oW + 4 * kAtom, oT = oG + 2 * kAtom, oS = oT + 2 * kAtom, oX = oS + 4 * kSAtom, oD = oX + 2 * 2048,
+              oBar = oD + kDstSlots * 512, kSmem = oBar + 16 * 8 + 16;
 enum { B_S_FULL = 0, B_S_EMPTY, B_G_FULL, B_A_FULL, B_A_EMPTY, B_DPRE_FULL, B_D_FULL0, B_D_FULL1, B_D_EMPTY0, B_D_EMPTY1 };
 constexpr uint32_t kColD = 0, kColDpre = 256, kColA = 384;
 
@@ -223,7 +226,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
                    const float* __restrict__ qnode, float* __restrict__ out, int out_by_slot, AggArgs agg, const __grid_constant__ LnParams lp) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
-  const uint32_t sW = sbase + oW, sG = sbase + oG, sT = sbase + oT, sS = sbase + oS, sX = sbase + oX, sBar = sbase + oBar;
+  const uint32_t sW = sbase + oW, sG = sbase + oG, sT = sbase + oT, sS = sbase + oS, sX = sbase + oX, sD = sbase + oD, sBar = sbase + oBar;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem_raw + oBar + 16 * 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
@@ -240,6 +243,8 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
   const long long n_rows = n_dst * k, split_rows = split_dst * k;      // both multiples of 128 by construction of the lists
   const long long n_tiles = (n_rows + 127) / 128;
   const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // destination rows are staged in shared memory when a tile can only span a few destinations (k >= 19); else read from global memory
+  const bool stage_dst = 128 / k + 2 <= kDstSlots;
   auto tile_class = [&](long long t) -> int { return ((long long)(blockIdx.x + t * (long long)gridDim.x) * 128 >= split_rows) ? 1 : 0; };
 
   // ---- one-time setup: weight image and the first tile's class table -> smem, barriers, TMEM
@@ -291,16 +296,17 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
     const uint32_t xslot = sX + (uint32_t)r * 4u;          // exchange slots of this row: set 0 (sums) / set 1 at +2048, quarter qq at + qq*512
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
     // metadata of this thread's row in tile `t` (s < 0: absent edge / padding destination / beyond the end)
+    // dst_: with staged destination rows the slot of the row's destination inside the tile's D block, else the destination node
     auto load_md = [&](long long t, int& s_, int& ty_, int& dst_, float& dist_) {
       s_ = -1; ty_ = 3; dst_ = 0; dist_ = 0.f;
       if (t < my_tiles) {
-        const long long idx = (blockIdx.x + t * (long long)gridDim.x) * 128 + r;
+        const long long idx0 = (blockIdx.x + t * (long long)gridDim.x) * 128, idx = idx0 + r;
         if (idx < n_rows) {
-          int j;
+          int j, j0;
           const unsigned a = row_dst(idx, j);
           const int d = row_nodes[a];
           if (d >= 0) {
-            dst_ = d;
+            dst_ = stage_dst ? (int)(a - row_dst(idx0, j0)) : d;
             const size_t e = (size_t)d * k + j;
             s_ = src[e]; ty_ = etype[e]; dist_ = dist_arr[e];
           }
@@ -345,13 +351,20 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       // ---- P[dst, offA + 32*qq ..] (rows of a warp usually share the destination: broadcast loads) stays in flight while we wait
       //      for the gathered source row in the staging tile
       float4 av[8];
+      if (!stage_dst) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) av[c] = __ldg(reinterpret_cast<const float4*>(P + (size_t)d0 * TD_NPROJ + offA + 32 * qq + 4 * c));
+        for (int c = 0; c < 8; ++c) {
+          av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) av[c] = __ldg(reinterpret_cast<const float4*>(P + (size_t)d0 * TD_NPROJ + offA + 32 * qq + 4 * c));
+        }
       }
       f2 x[16];
       mbar_wait(bar(B_S_FULL), ph);
+      if (stage_dst) {                  // the destination row quarter from the staged D block (rows of a warp mostly share it: broadcast reads)
+        const uint32_t d_row = sD + (uint32_t)d0 * 512u + (uint32_t)qq * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) av[c] = lds128(d_row + 16u * c);
+      }
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const float4 v = lds128(s_row + 16u * c);
@@ -379,7 +392,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       if (it + 1 < my_tiles) write_g(s1, t1, dist1);
       s0 = s1; t0 = t1; d0 = d1; dist0 = dist1;
       load_md(it + 2, s1, t1, d1, dist1);
-      if (s0 >= 0) prefetch_l1(P + (size_t)d0 * TD_NPROJ + offA + 32 * qq);      // next tile's destination row quarter -> L1
+      if (!stage_dst && s0 >= 0) prefetch_l1(P + (size_t)d0 * TD_NPROJ + offA + 32 * qq);      // next tile's destination row quarter -> L1
       // ---- LayerNorm over the 128 features of the row: 4 threads (feature quarters) exchange partial sums through smem.
       //      Slot set 0 is rewritten only after every thread passed this tile's second barrier, set 1 only after the next tile's first.
       f2 sa = add2(x[0], x[1]), sb = add2(x[2], x[3]), sc = add2(x[4], x[5]), sd = add2(x[6], x[7]);
@@ -516,6 +529,20 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
           const uint32_t dsta = sS + (uint32_t)atom * kSAtom + (uint32_t)row * kSRow + (uint32_t)(ch << 4);
           if (sr >= 0) cp_async16(dsta, P + (size_t)sr * TD_NPROJ + offB + 4 * lane);
           else sts128f(dsta, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        if (stage_dst) {
+          // ---- the tile's destination rows P[dst, offA + 4*lane ..] -> D (512 B each); absent rows read zeros through S, so padding
+          //      destinations only need defined bytes
+          const long long idx0 = (blockIdx.x + it * (long long)gridDim.x) * 128;
+          int j0;
+          const unsigned a0 = row_dst(idx0, j0);
+          for (int d = gw; d < kDstSlots; d += kGatherWarps) {
+            const long long a = (long long)a0 + d;
+            const int dn = (a < n_dst && a * k < idx0 + 128) ? row_nodes[a] : -1;
+            const uint32_t dsta = sD + (uint32_t)d * 512u + (uint32_t)(lane << 4);
+            if (dn >= 0) cp_async16(dsta, P + (size_t)dn * TD_NPROJ + offA + 4 * lane);
+            else sts128f(dsta, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
         }
         cp_async_wait_all();
         __syncwarp();

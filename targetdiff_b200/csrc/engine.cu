@@ -69,6 +69,11 @@ struct tdiff_engine {
   const float *w_prot = nullptr, *b_prot = nullptr, *wl_t = nullptr, *bl = nullptr;
   const float *ew_w1t = nullptr, *ew_b1 = nullptr, *ew_g = nullptr, *ew_b = nullptr, *ew_w2 = nullptr, *ew_off = nullptr;
   float ew_b2 = 0.f, ew_coeff = -0.5f;
+  // config-surface options (tdiff_config): blocks, edge-gate flavour, node_output MLP, time embedding
+  int num_blocks = 1, ew_mode = 0 /* 0 global, 1 'r', 2 'm', 3 none */, out_fc = 0, time_emb = 0;
+  const float* w_time = nullptr;        // time_emb 'simple': the ligand embedding's extra input column
+  const float* zeros128 = nullptr;
+  DevBuf ew_x2h, ew_h2x, hagg, time_norm;   // 'r' gates per slot (per layer, both sub-layers); x2h aggregate for node_output; t / T per graph
   const float *hd_w1t = nullptr, *hd_b1 = nullptr, *hd_w2 = nullptr, *hd_b2 = nullptr;
   const float *t_c0 = nullptr, *t_ct = nullptr, *t_logvar = nullptr, *t_la = nullptr, *t_l1ma = nullptr, *t_lca = nullptr, *t_l1mca = nullptr,
               *t_sra = nullptr, *t_srm1 = nullptr;
@@ -86,6 +91,15 @@ struct tdiff_engine {
   DevBuf x2h_rows, lig_rows, rel_rows, rel_counts;
   long long x2h_n_dst = 0, x2h_split = 0, lig_n_dst = 0;
   int row_pad = 4;                      // destinations per class are padded so that class boundaries fall on 128-row tile boundaries
+  // Ligand-free cache (exact): protein atoms never move and their embedding is step-invariant, so a protein node that is neither
+  // touched by a ligand atom nor (transitively, layer by layer) fed by a touched node has the same features after x2h layer l in
+  // every denoising step.  Those values are computed once per bound batch (h_free[l]); per step the first `free_depth` x2h layers
+  // only visit the dirty destinations (free_rows[l]) and the clean rows are restored from the cache.
+  int free_depth = 0;                   // cached x2h layers of this batch (0 = off)
+  int env_free_depth = 2;               // TDIFF_FREE_DEPTH (default 2; 0 disables)
+  bool free_ready = false;
+  DevBuf h_free, dirty, free_rows, free_counts, lig_save;
+  long long free_stride = 0;            // ints per layer in free_rows
   DevBuf xm0, xm1, offset, h0, h, P, q, src, src_prev, etype, e_w, dist, kbuf, vbuf, v16, lig_pos, lig_v, logits;
   DevBuf step, err_flag, node_off, total_edges;
   DevBuf stage[8];   // staging for tdiff_sample_host
@@ -206,7 +220,50 @@ bool pack_edge_mlp(Packer& pk, const std::string& p, int nout, MlpOff& o, const 
   return true;
 }
 
-struct SubOff { size_t wn_t, bn; long long wn_img; MlpOff k, v, q; };
+struct SubOff {
+  size_t wn_t, bn; long long wn_img; MlpOff k, v, q;
+  long long ew_w = -1; float ew_b = 0.f;                       // ew_net_type 'r' / 'm'
+  long long out_wa = -1, out_wb = -1, out_w2 = -1, out_b1 = -1, out_g = -1, out_b = -1, out_b2 = -1;   // x2h_out_fc node_output MLP
+};
+
+// optional per-sub-layer parameters: the 'r' / 'm' gate Linear and the node_output MLP (reference models/uni_transformer.py:34-40)
+bool pack_sublayer_options(Packer& pk, const std::string& p, int ew_dim, bool out_fc, SubOff& so) {
+  if (ew_dim > 0) {
+    const float* w = pk.get(p + ".ew_net.0.weight", ew_dim);
+    const float* b = pk.get(p + ".ew_net.0.bias", 1);
+    if (!w || !b) return false;
+    so.ew_w = (long long)pk.alloc(ew_dim);
+    memcpy(&pk.host[so.ew_w], w, ew_dim * sizeof(float));
+    so.ew_b = b[0];
+  }
+  if (out_fc) {
+    const std::string np = p + ".node_output";
+    const float* w1 = pk.get(np + ".net.0.weight", (int64_t)TD_H * 2 * TD_H);
+    const float* b1 = pk.get(np + ".net.0.bias", TD_H);
+    const float* g = pk.get(np + ".net.1.weight", TD_H);
+    const float* b = pk.get(np + ".net.1.bias", TD_H);
+    const float* w2 = pk.get(np + ".net.3.weight", (int64_t)TD_H * TD_H);
+    const float* b2 = pk.get(np + ".net.3.bias", TD_H);
+    if (!w1 || !b1 || !g || !b || !w2 || !b2) return false;
+    std::vector<float> blk((size_t)TD_H * TD_H);
+    for (int half = 0; half < 2; ++half) {                     // input columns [aggregate | h]
+      for (int n = 0; n < TD_H; ++n)
+        for (int kk = 0; kk < TD_H; ++kk) blk[(size_t)n * TD_H + kk] = w1[(size_t)n * 2 * TD_H + half * TD_H + kk];
+      long long& dst = half == 0 ? so.out_wa : so.out_wb;
+      dst = (long long)pk.img.size();
+      pk.img.resize(pk.img.size() + 3 * 32768, 0);
+      pack_umma_image(blk.data(), pk.img, (size_t)dst);
+    }
+    so.out_w2 = (long long)pk.img.size();
+    pk.img.resize(pk.img.size() + 3 * 32768, 0);
+    pack_umma_image(w2, pk.img, (size_t)so.out_w2);
+    so.out_b1 = (long long)pk.alloc(TD_H); memcpy(&pk.host[so.out_b1], b1, TD_H * 4);
+    so.out_g = (long long)pk.alloc(TD_H); memcpy(&pk.host[so.out_g], g, TD_H * 4);
+    so.out_b = (long long)pk.alloc(TD_H); memcpy(&pk.host[so.out_b], b, TD_H * 4);
+    so.out_b2 = (long long)pk.alloc(TD_H); memcpy(&pk.host[so.out_b2], b2, TD_H * 4);
+  }
+  return true;
+}
 
 bool pack_sublayer(Packer& pk, const std::string& p, const char* kn, const char* vn, const char* qn, int nout_v, SubOff& so) {
   const int KV = 4 + 4 * TD_NG + 2 * TD_H;
@@ -280,6 +337,10 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     return set_err(TDIFF_EINVAL, "model_mean_type=%d (0 = C0, 1 = noise)", cfg->model_mean_type);
   for (int r : cfg->reserved)
     if (r != 0) return set_err(TDIFF_EINVAL, "tdiff_config.reserved must be 0");
+  if (cfg->num_blocks < 0 || cfg->num_blocks > 16 || cfg->ew_net_type < 0 || cfg->ew_net_type > 3 || (cfg->x2h_out_fc != 0 && cfg->x2h_out_fc != 1) ||
+      (cfg->time_emb != 0 && cfg->time_emb != 1))
+    return set_err(TDIFF_EINVAL, "bad option (num_blocks=%d ew_net_type=%d x2h_out_fc=%d time_emb=%d)", cfg->num_blocks, cfg->ew_net_type,
+                   cfg->x2h_out_fc, cfg->time_emb);
   if (cfg->num_layers < 1 || cfg->num_classes < 1 || cfg->num_classes > TD_CMAX || cfg->protein_feat_dim < 1 || cfg->num_timesteps < 1)
     return set_err(TDIFF_EINVAL, "bad config (num_layers=%d num_classes=%d protein_feat_dim=%d num_timesteps=%d)", cfg->num_layers,
                    cfg->num_classes, cfg->protein_feat_dim, cfg->num_timesteps);
@@ -296,6 +357,7 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
 
   tdiff_engine* e = new tdiff_engine();
   e->cfg = *cfg; e->device = device; e->sm_count = prop.multiProcessorCount; e->K = cfg->knn;
+  e->num_blocks = cfg->num_blocks > 1 ? cfg->num_blocks : 1; e->ew_mode = cfg->ew_net_type; e->out_fc = cfg->x2h_out_fc; e->time_emb = cfg->time_emb;
 
   Packer pk;
   for (int i = 0; i < n_entries; ++i)
@@ -312,26 +374,32 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
   // embeddings
   const float* wp = pk.get("protein_atom_emb.weight", (int64_t)(TD_H - 1) * F);
   const float* bp = pk.get("protein_atom_emb.bias", TD_H - 1);
-  const float* wl = pk.get("ligand_atom_emb.weight", (int64_t)(TD_H - 1) * KC);
+  const int KIN = KC + (cfg->time_emb ? 1 : 0);           // ligand embedding input width: classes (+ the time column)
+  const float* wl = pk.get("ligand_atom_emb.weight", (int64_t)(TD_H - 1) * KIN);
   const float* blp = pk.get("ligand_atom_emb.bias", TD_H - 1);
-  size_t o_wp = pk.alloc((size_t)TD_H * F), o_bp = pk.alloc(TD_H), o_wl = pk.alloc((size_t)KC * TD_H), o_bl = pk.alloc(TD_H);
+  size_t o_wp = pk.alloc((size_t)TD_H * F), o_bp = pk.alloc(TD_H), o_wl = pk.alloc((size_t)KC * TD_H), o_bl = pk.alloc(TD_H),
+         o_wtime = pk.alloc(TD_H), o_zeros = pk.alloc(TD_H);
   if (wp && bp && wl && blp) {
     memcpy(&pk.host[o_wp], wp, (size_t)(TD_H - 1) * F * sizeof(float));
     memcpy(&pk.host[o_bp], bp, (TD_H - 1) * sizeof(float));
     for (int v = 0; v < KC; ++v)
-      for (int f = 0; f < TD_H - 1; ++f) pk.host[o_wl + (size_t)v * TD_H + f] = wl[(size_t)f * KC + v];
+      for (int f = 0; f < TD_H - 1; ++f) pk.host[o_wl + (size_t)v * TD_H + f] = wl[(size_t)f * KIN + v];
+    if (cfg->time_emb)
+      for (int f = 0; f < TD_H - 1; ++f) pk.host[o_wtime + f] = wl[(size_t)f * KIN + KC];
     memcpy(&pk.host[o_bl], blp, (TD_H - 1) * sizeof(float));
   }
   // global edge gate (models/uni_transformer.py:242-243,312-316)
-  const float* gw1 = pk.get("refine_net.edge_pred_layer.net.0.weight", (int64_t)TD_H * TD_NG);
-  const float* gb1 = pk.get("refine_net.edge_pred_layer.net.0.bias", TD_H);
-  const float* gg = pk.get("refine_net.edge_pred_layer.net.1.weight", TD_H);
-  const float* gb = pk.get("refine_net.edge_pred_layer.net.1.bias", TD_H);
-  const float* gw2 = pk.get("refine_net.edge_pred_layer.net.3.weight", TD_H);
-  const float* gb2 = pk.get("refine_net.edge_pred_layer.net.3.bias", 1);
+  const bool has_gate = cfg->ew_net_type == 0;            // the edge_pred_layer only exists for ew_net_type 'global' (uni_transformer.py:242-243)
+  const float* gw1 = has_gate ? pk.get("refine_net.edge_pred_layer.net.0.weight", (int64_t)TD_H * TD_NG) : nullptr;
+  const float* gb1 = has_gate ? pk.get("refine_net.edge_pred_layer.net.0.bias", TD_H) : nullptr;
+  const float* gg = has_gate ? pk.get("refine_net.edge_pred_layer.net.1.weight", TD_H) : nullptr;
+  const float* gb = has_gate ? pk.get("refine_net.edge_pred_layer.net.1.bias", TD_H) : nullptr;
+  const float* gw2 = has_gate ? pk.get("refine_net.edge_pred_layer.net.3.weight", TD_H) : nullptr;
+  const float* gb2 = has_gate ? pk.get("refine_net.edge_pred_layer.net.3.bias", 1) : nullptr;
   const float* goff = pk.get("refine_net.distance_expansion.offset", TD_NG);
   size_t o_gw1 = pk.alloc((size_t)TD_NG * TD_H), o_gb1 = pk.alloc(TD_H), o_gg = pk.alloc(TD_H), o_gb = pk.alloc(TD_H), o_gw2 = pk.alloc(TD_H),
          o_goff = pk.alloc(TD_NG);
+  if (goff) memcpy(&pk.host[o_goff], goff, TD_NG * 4);
   if (gw1 && gb1 && gg && gb && gw2 && gb2 && goff) {
     for (int j = 0; j < TD_NG; ++j)
       for (int f = 0; f < TD_H; ++f) pk.host[o_gw1 + (size_t)j * TD_H + f] = gw1[(size_t)f * TD_NG + j];
@@ -360,6 +428,8 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     const std::string p = "refine_net.base_block." + std::to_string(l);
     if (!pack_sublayer(pk, p + ".x2h_layers.0", "hk_func", "hv_func", "hq_func", TD_H, sx[l])) break;
     if (!pack_sublayer(pk, p + ".h2x_layers.0", "xk_func", "xv_func", "xq_func", TD_HEADS, sh[l])) break;
+    if (!pack_sublayer_options(pk, p + ".x2h_layers.0", cfg->ew_net_type == 1 ? 4 * TD_NG : cfg->ew_net_type == 2 ? TD_H : 0, cfg->x2h_out_fc != 0, sx[l])) break;
+    if (!pack_sublayer_options(pk, p + ".h2x_layers.0", cfg->ew_net_type == 1 ? 4 * TD_NG : 0, false, sh[l])) break;
     const float* off = pk.get(p + ".distance_expansion.offset", TD_NG);
     o_off[l] = pk.alloc(TD_NG);
     if (off) {
@@ -390,10 +460,15 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     else if (!strcmp(mode, "tc6")) e->mlp_mode = 3;
     else { cudaFree(e->arena); cudaFree(e->img_arena); delete e; return set_err(TDIFF_EINVAL, "TDIFF_EDGE_MLP=%s (simt|tc3|tc3v2|tc6)", mode); }
   }
+  if ((cfg->ew_net_type != 0 || cfg->x2h_out_fc) && !(e->mlp_mode == 2 && e->mlp_v4)) {
+    cudaFree(e->arena); cudaFree(e->img_arena); delete e;
+    return set_err(TDIFF_EINVAL, "ew_net_type != 'global' and x2h_out_fc are implemented by the default engine mode only (unset TDIFF_EDGE_MLP)");
+  }
   e->env_no_fused_agg = getenv("TDIFF_NO_FUSED_AGG") != nullptr;
   e->env_no_restrict = getenv("TDIFF_NO_RESTRICT") != nullptr;
   e->env_no_graph = getenv("TDIFF_NO_GRAPH") != nullptr;
   e->env_knn_full = getenv("TDIFF_KNN_FULL") != nullptr;
+  if (const char* fd = getenv("TDIFF_FREE_DEPTH")) e->env_free_depth = atoi(fd) < 0 ? 0 : (atoi(fd) > 8 ? 8 : atoi(fd));
   e->host_arena = pk.host;
   const float* A = e->arena;
   const unsigned char* IM = e->img_arena;
@@ -401,6 +476,7 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
   e->t_l1ma = A + tabs[4].off; e->t_lca = A + tabs[5].off; e->t_l1mca = A + tabs[6].off;
   e->t_sra = A + tabs[7].off; e->t_srm1 = A + tabs[8].off;
   e->w_prot = A + o_wp; e->b_prot = A + o_bp; e->wl_t = A + o_wl; e->bl = A + o_bl;
+  e->w_time = cfg->time_emb ? A + o_wtime : nullptr; e->zeros128 = A + o_zeros;
   e->ew_w1t = A + o_gw1; e->ew_b1 = A + o_gb1; e->ew_g = A + o_gg; e->ew_b = A + o_gb; e->ew_w2 = A + o_gw2; e->ew_off = A + o_goff;
   e->hd_w1t = A + o_hw1; e->hd_b1 = A + o_hb1; e->hd_w2 = A + o_hw2; e->hd_b2 = A + o_hb2;
   e->layers.resize(L);
@@ -411,6 +487,17 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     ly.x2h.k = mk_mlp(A, IM, sx[l].k, 0, 256); ly.x2h.v = mk_mlp(A, IM, sx[l].v, 128, 384); ly.x2h.q = mk_mlp(A, IM, sx[l].q, 512, 512);
     ly.h2x.wn_t = A + sh[l].wn_t; ly.h2x.bn = A + sh[l].bn; ly.h2x.wn_img = IM ? IM + sh[l].wn_img : nullptr;
     ly.h2x.k = mk_mlp(A, IM, sh[l].k, 0, 256); ly.h2x.v = mk_mlp(A, IM, sh[l].v, 128, 384); ly.h2x.q = mk_mlp(A, IM, sh[l].q, 512, 512);
+    for (int sub = 0; sub < 2; ++sub) {
+      TdSubLayer& sl = sub ? ly.h2x : ly.x2h;
+      const SubOff& so = sub ? sh[l] : sx[l];
+      sl.ew_w = so.ew_w >= 0 ? A + so.ew_w : nullptr; sl.ew_b = so.ew_b;
+      sl.out_wa_img = so.out_wa >= 0 ? IM + so.out_wa : nullptr; sl.out_wb_img = so.out_wb >= 0 ? IM + so.out_wb : nullptr;
+      sl.out_b1 = so.out_b1 >= 0 ? A + so.out_b1 : nullptr;
+      memset(&sl.out, 0, sizeof(sl.out));
+      if (so.out_w2 >= 0) {
+        sl.out.w2_img = IM + so.out_w2; sl.out.ln_g = A + so.out_g; sl.out.ln_b = A + so.out_b; sl.out.b2 = A + so.out_b2; sl.out.nout = TD_H;
+      }
+    }
   }
   if (e->step.ensure(sizeof(int)) || e->err_flag.ensure(sizeof(int)) || e->total_edges.ensure(sizeof(long long))) {
     tdiff_destroy(e); return set_err(TDIFF_ECUDA, "cudaMalloc failed");
@@ -433,7 +520,7 @@ extern "C" void tdiff_destroy(tdiff_engine* e) {
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   DevBuf* bufs[] = {&e->node_ptr, &e->prot_ptr, &e->prot_node, &e->prot_graph, &e->lig_node, &e->lig_graph, &e->node_lig, &e->xm0, &e->xm1,
-                    &e->rel_flag, &e->rel_list, &e->n_rel, &e->work_list, &e->n_work, &e->knn_cache, &e->x2h_rows, &e->lig_rows, &e->rel_rows, &e->rel_counts, &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->src_prev, &e->etype, &e->e_w, &e->dist, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
+                    &e->rel_flag, &e->rel_list, &e->n_rel, &e->work_list, &e->n_work, &e->knn_cache, &e->x2h_rows, &e->lig_rows, &e->rel_rows, &e->rel_counts, &e->ew_x2h, &e->ew_h2x, &e->hagg, &e->time_norm, &e->h_free, &e->dirty, &e->free_rows, &e->free_counts, &e->lig_save, &e->offset, &e->h0, &e->h, &e->P, &e->q, &e->src, &e->src_prev, &e->etype, &e->e_w, &e->dist, &e->kbuf, &e->vbuf, &e->v16, &e->lig_pos,
                     &e->lig_v, &e->logits, &e->step, &e->err_flag, &e->node_off, &e->total_edges};
   for (auto* b : bufs) b->release();
   for (auto& b : e->stage) b.release();
@@ -493,10 +580,25 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
                  e->rel_counts.ensure(16);
   // per-edge buffers: v4 keeps 16 attention logits / weights per row and, with the aggregation fused into the value launch (k == 32),
   // no [E,128] tensor at all; the earlier execution modes materialise keys and values
-  const bool fuse = v4 && K == 32 && !e->env_no_fused_agg;
+  const bool fuse = v4 && K == 32 && !e->env_no_fused_agg && e->ew_mode != 2;      // 'm' gates need the value rows (unfused aggregation)
+  if (e->ew_mode == 1) bad |= e->ew_x2h.ensure(slots * 4) | e->ew_h2x.ensure(slots * 4);
+  if (e->out_fc) bad |= e->hagg.ensure((size_t)N * TD_H * 4);
+  if (e->time_emb) bad |= e->time_norm.ensure((size_t)B * 4 + 16);
   bad |= e->kbuf.ensure(v4 ? (size_t)(nPpad + nLpad) * K * TD_HEADS * 4 + 64 : slots * TD_H * 4);
   if (!fuse) bad |= e->vbuf.ensure(slots * TD_H * 4);
   bad |= e->v16.ensure((size_t)nLpad * K * TD_HEADS * 4 + 16);
+  // ligand-free cache: needs the fused path and, in every graph, more than k protein atoms (so that parked ligand atoms can never be
+  // among a protein atom's neighbours) and at least one ligand atom
+  int min_pc = 1 << 30;
+  for (int g = 0; g < B; ++g) if (pc[g] < min_pc) min_pc = pc[g];
+  e->free_ready = false;
+  e->free_depth = (fuse && Nl > 0 && min_pc > K) ? e->env_free_depth : 0;      // (only block 0 of a multi-block network uses it)
+  if (e->free_depth > (int)e->layers.size() - 1) e->free_depth = (int)e->layers.size() - 1;
+  if (e->free_depth > 0)
+    bad |= e->h_free.ensure((size_t)e->free_depth * N * TD_H * 4) | e->dirty.ensure((size_t)e->free_depth * N + 16) |
+           e->free_rows.ensure((size_t)e->free_depth * x2h_rows.size() * 4 + 4) | e->free_counts.ensure((size_t)e->free_depth * 16) |
+           e->lig_save.ensure((size_t)Nl * 20 + 32);
+  e->free_stride = (long long)x2h_rows.size();
   bad |= e->lig_pos.ensure(Nl * 16 + 16) | e->lig_v.ensure(Nl * 4 + 4) | e->logits.ensure((size_t)Nl * e->cfg.num_classes * 4 + 4);
   bad |= e->node_off.ensure(N * 8) | e->rel_flag.ensure(N + 16) | e->rel_list.ensure(N * 4 + 64) | e->n_rel.ensure(16) | e->work_list.ensure(N * 4 + 64) | e->n_work.ensure(16);
   e->knn_incremental = !e->env_knn_full && Np > 0;
@@ -519,6 +621,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   }
   CK(cudaStreamSynchronize(st));   // host vectors go out of scope
   CK(cudaMemsetAsync(e->offset.p, 0, (size_t)B * 16, st));
+  if (e->time_emb) CK(cudaMemsetAsync(e->time_norm.p, 0, (size_t)B * 4, st));
   CK(cudaMemsetAsync(e->h0.p, 0, (size_t)N * TD_H * 4, st));
   CK(cudaMemsetAsync(e->xm0.p, 0, (size_t)N * 16, st));
   CK(cudaMemsetAsync(e->xm1.p, 0, (size_t)N * 16, st));
@@ -596,17 +699,22 @@ struct Prof {
 enum RowList { ROWS_ALL = 0, ROWS_LIGAND = 1, ROWS_RELEVANT = 2 };
 bool fused_logits(const tdiff_engine* e) { return e->mlp_mode == 2 && e->mlp_v4; }
 void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src, const unsigned char* etype, RowList list, int K, const TdMlp& m,
-              const float* offsets, float coeff, float* out, cudaStream_t st, const float* qnode = nullptr, const float* agg_logits = nullptr,
-              float* agg_h = nullptr, int key_softmax = 0) {
+              const float* offsets, float coeff, float* out, cudaStream_t st, const float* e_w, const float* qnode = nullptr,
+              const float* agg_logits = nullptr, float* agg_h = nullptr, int key_softmax = 0, int free_layer = -1) {
   if (fused_logits(e) && m.w2_img && m.tabcls_img) {
     const int* rows = list == ROWS_ALL ? e->x2h_rows.as<int>() : list == ROWS_LIGAND ? e->lig_rows.as<int>() : e->rel_rows.as<int>();
+    const int* counts = list == ROWS_RELEVANT ? e->rel_counts.as<int>() : nullptr;
+    if (free_layer >= 0) {           // ligand-free cache: only the dirty destinations of this layer (device-compacted, class-sorted)
+      rows = e->free_rows.as<int>() + (size_t)free_layer * e->free_stride;
+      counts = e->free_counts.as<int>() + 4 * free_layer;
+    }
     const long long n_dst = list == ROWS_LIGAND ? e->lig_n_dst : e->x2h_n_dst;          // ROWS_RELEVANT: upper bound, real counts on the device
     const long long split = list == ROWS_LIGAND ? 0 : e->x2h_split;
     // plain (unfused) x2h outputs are consumed by slot index (aggregate_h_logits_kernel); everything else by row index
     const int by_slot = (list != ROWS_LIGAND && !key_softmax && agg_logits == nullptr) ? 1 : 0;
-    td_launch_edge_mlp_v4(P, src, etype, e->dist.as<float>(), rows, n_dst, split, list == ROWS_RELEVANT ? e->rel_counts.as<int>() : nullptr, K, m,
+    td_launch_edge_mlp_v4(P, src, etype, e->dist.as<float>(), rows, n_dst, split, counts, K, m,
                           offsets, coeff, e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena),
-                          e->host_arena.data() + (m.b2 - e->arena), qnode, out, by_slot, agg_logits, e->e_w.as<float>(), agg_h, key_softmax,
+                          e->host_arena.data() + (m.b2 - e->arena), qnode, out, by_slot, agg_logits, e_w, agg_h, key_softmax,
                           e->sm_count, st);
     return;
   }
@@ -634,7 +742,8 @@ void node_side(tdiff_engine* e, const float* h, int N, const TdSubLayer& sl, flo
 }
 
 // One evaluation of the network on the bound batch (reference ScorePosNet3D.forward -> UniTransformerO2TwoUpdateGeneral.forward)
-void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
+// `free_build` > 0: ligand-free cache construction -- only the first `free_build` x2h layers, features saved after each (ligand parked far away)
+void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x, int free_build = 0) {
   const int N = e->N, Nl = e->Nl, K = e->K;
   float4* xm[2] = {e->xm0.as<float4>(), e->xm1.as<float4>()};
   const int* src = e->src.as<int>();
@@ -643,66 +752,123 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
   float* P = e->P.as<float>();
   float* q = e->q.as<float>();
   td_launch_scatter_ligand_pos(e->lig_pos.as<float4>(), e->lig_node.as<int>(), Nl, xm[0], st);
-  td_launch_init_h(e->h0.as<float>(), xm[0], e->lig_v.as<int>(), e->node_lig.as<int>(), e->wl_t, e->bl, N, h, st);
-  if (e->knn_incremental)
-    td_launch_knn_update(xm[0], e->node_ptr.as<int>(), e->prot_ptr.as<int>(), e->B, e->max_ng, K, e->knn_cache.as<unsigned long long>(), e->src.as<int>(), st);
-  else
-    td_launch_knn(xm[0], e->node_ptr.as<int>(), e->B, e->max_ng, K, e->src.as<int>(), st);
-  td_launch_edge_const(xm[0], src, e->src_prev.as<int>(), e->have_prev ? 1 : 0, N, K, e->ew_off, e->ew_coeff, e->ew_w1t, e->ew_b1, e->ew_g, e->ew_b, e->ew_w2, e->ew_b2,
-                       e->etype.as<unsigned char>(), e->e_w.as<float>(), e->rel_flag.as<unsigned char>(), e->work_list.as<int>(), e->n_work.as<int>(), st);
-  td_launch_rel_compact(e->rel_flag.as<unsigned char>(), N, e->rel_list.as<int>(), e->n_rel.as<int>(), st);
-  e->launches += 5;
-  if (fused_logits(e) && e->restrict_last) {       // class-sorted list of the relevant destinations for the last layer's x2h
-    td_launch_rel_rows(e->rel_flag.as<unsigned char>(), xm[0], N, e->lig_rows.as<int>(), (int)e->lig_n_dst, e->row_pad, e->rel_rows.as<int>(),
-                       e->rel_counts.as<int>(), st);
-    e->launches += 2;
-  }
+  td_launch_init_h(e->h0.as<float>(), xm[0], e->lig_v.as<int>(), e->node_lig.as<int>(), e->wl_t, e->bl, e->w_time, e->time_norm.as<float>(),
+                   e->lig_graph.as<int>(), N, h, st);
+  e->launches += 2;
   int cur = 0;
-  for (size_t l = 0; l < e->layers.size(); ++l) {
-    const TdLayer& ly = e->layers[l];
-    // ---- x2h: h <- h + sum_e alpha * v * e_w
-    node_side(e, h, N, ly.x2h, P, q, st);
-    if (e->mlp_mode != 0) { td_launch_edge_geom(xm[cur], src, N, K, e->dist.as<float>(), st); e->launches += 1; }
-    // k == 32: a 128-row tile is 4 complete destinations -> the value launch also performs the softmax aggregation (h += ...)
-    const bool fuse_agg = fused_logits(e) && K == 32 && !e->env_no_fused_agg;
-    // sampling loop, last layer: only the ligand atoms' features feed the type head and only ligand atoms + their neighbours feed
-    // the last h2x, so x2h is evaluated for those destinations only (device-compacted list; final_h of other nodes is not produced)
-    const bool sub = fuse_agg && e->restrict_last && l + 1 == e->layers.size() && !e->env_no_restrict;
-    const RowList rl = sub ? ROWS_RELEVANT : ROWS_ALL;
-    {
-      Prof pr(e, st, EV_EDGE_MLP);
-      edge_mlp(e, P, xm[cur], src, etype, rl, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st, fused_logits(e) ? q : nullptr, nullptr,
-               nullptr, fuse_agg ? 1 : 0);
-      edge_mlp(e, P, xm[cur], src, etype, rl, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), st, nullptr,
-               fuse_agg ? e->kbuf.as<float>() : nullptr, fuse_agg ? h : nullptr);
+  const int n_blocks = free_build ? 1 : e->num_blocks;
+  for (int blk = 0; blk < n_blocks; ++blk) {
+    // ---- graph of this block from the current coordinates (reference models/uni_transformer.py:306-318)
+    const int use_free = (!free_build && e->free_ready && blk == 0) ? e->free_depth : 0;
+    const bool last_blk = blk + 1 == n_blocks;
+    if (e->knn_incremental)
+      td_launch_knn_update(xm[cur], e->node_ptr.as<int>(), e->prot_ptr.as<int>(), e->B, e->max_ng, K, e->knn_cache.as<unsigned long long>(), e->src.as<int>(), st);
+    else
+      td_launch_knn(xm[cur], e->node_ptr.as<int>(), e->B, e->max_ng, K, e->src.as<int>(), st);
+    td_launch_edge_const(xm[cur], src, e->src_prev.as<int>(), e->have_prev ? 1 : 0, N, K, e->ew_off, e->ew_coeff, e->ew_w1t, e->ew_b1, e->ew_g, e->ew_b, e->ew_w2,
+                         e->ew_b2, e->etype.as<unsigned char>(), e->e_w.as<float>(), e->rel_flag.as<unsigned char>(),
+                         use_free ? e->dirty.as<unsigned char>() : nullptr, e->work_list.as<int>(), e->n_work.as<int>(), e->ew_mode != 0 ? 1 : 0, st);
+    e->have_prev = true;
+    for (int l = 0; l < use_free; ++l) {             // dirty sets layer by layer and their class-sorted destination lists
+      unsigned char* dl = e->dirty.as<unsigned char>() + (size_t)l * N;
+      if (l > 0) td_launch_dirty_propagate(dl - N, src, N, K, dl, st);
+      td_launch_rel_rows(dl, xm[cur], N, e->lig_rows.as<int>(), (int)e->lig_n_dst, e->row_pad, e->free_rows.as<int>() + (size_t)l * e->free_stride,
+                         e->free_counts.as<int>() + 4 * l, st);
+      e->launches += l > 0 ? 3 : 2;
     }
-    if (!fuse_agg) {
-      Prof pr(e, st, EV_AGG_H);
-      if (fused_logits(e)) td_launch_aggregate_h_logits(e->kbuf.as<float>(), e->vbuf.as<float>(), e->e_w.as<float>(), src, h, h, N, K, st);
-      else td_launch_aggregate_h(e->kbuf.as<float>(), e->vbuf.as<float>(), e->e_w.as<float>(), src, q, h, h, N, K, st);
+    td_launch_rel_compact(e->rel_flag.as<unsigned char>(), N, e->rel_list.as<int>(), e->n_rel.as<int>(), st);
+    e->launches += 4;
+    if (fused_logits(e) && e->restrict_last && last_blk) {       // class-sorted list of the relevant destinations for the last x2h
+      td_launch_rel_rows(e->rel_flag.as<unsigned char>(), xm[cur], N, e->lig_rows.as<int>(), (int)e->lig_n_dst, e->row_pad, e->rel_rows.as<int>(),
+                         e->rel_counts.as<int>(), st);
+      e->launches += 2;
     }
-    e->launches += fuse_agg ? 4 : 5;
-    if (fix_x || Nl == 0) continue;     // h2x only moves ligand atoms; with fix_x its result is discarded (:204-206)
-    // ---- h2x: x_lig <- x_lig + mean_heads sum_e alpha * v * e_w * (x_dst - x_src), destinations = ligand atoms only
-    {
-      const bool rel = fused_logits(e) && !e->env_no_restrict;      // h2x only reads P / q of ligand atoms and their neighbours
-      node_side(e, h, N, ly.h2x, P, q, st, rel ? e->rel_list.as<int>() : nullptr, rel ? e->n_rel.as<int>() : nullptr);
+    const float4* xm_blk = xm[cur];                  // coordinates the block's graph was built from (protein flags for the cache kernels)
+    const size_t n_layers = free_build ? (size_t)free_build : e->layers.size();
+    for (size_t l = 0; l < n_layers; ++l) {
+      const TdLayer& ly = e->layers[l];
+      const int fl = (int)l < use_free ? (int)l : -1;
+      // per-sub-layer edge gates: the global gate, or the layer's own 'r' gates (evaluated with the edge lengths), or 1
+      const float* ew_x = e->ew_mode == 1 ? e->ew_x2h.as<float>() : e->e_w.as<float>();
+      const float* ew_h = e->ew_mode == 1 ? e->ew_h2x.as<float>() : e->e_w.as<float>();
+      // ---- x2h: h <- h + sum_e alpha * v * e_w   (+ node_output MLP with x2h_out_fc)
+      node_side(e, h, N, ly.x2h, P, q, st);
+      if (e->mlp_mode != 0) {
+        TdEwR ew = {nullptr, nullptr, 0.f, 0.f, ly.offsets, ly.coeff, nullptr, nullptr};
+        if (e->ew_mode == 1) { ew.w_x2h = ly.x2h.ew_w; ew.w_h2x = ly.h2x.ew_w; ew.b_x2h = ly.x2h.ew_b; ew.b_h2x = ly.h2x.ew_b; ew.out_x2h = e->ew_x2h.as<float>(); ew.out_h2x = e->ew_h2x.as<float>(); }
+        td_launch_edge_geom(xm[cur], src, etype, N, K, e->dist.as<float>(), ew, st);
+        e->launches += 1;
+      }
+      // k == 32: a 128-row tile is 4 complete destinations -> the value launch also performs the softmax aggregation (h += ...)
+      const bool fuse_agg = fused_logits(e) && K == 32 && !e->env_no_fused_agg && e->ew_mode != 2;
+      // sampling loop, last layer: only the ligand atoms' features feed the type head and only ligand atoms + their neighbours feed
+      // the last h2x, so x2h is evaluated for those destinations only (device-compacted list; final_h of other nodes is not produced)
+      const bool sub = fuse_agg && e->restrict_last && last_blk && l + 1 == e->layers.size() && !e->env_no_restrict && !e->out_fc;
+      const RowList rl = sub ? ROWS_RELEVANT : ROWS_ALL;
+      float* agg_target = h;
+      if (e->out_fc) {               // node_output needs the bare aggregate: accumulate into a zeroed buffer instead of h
+        agg_target = e->hagg.as<float>();
+        cudaMemsetAsync(agg_target, 0, (size_t)N * TD_H * 4, st);
+      }
+      {
+        Prof pr(e, st, EV_EDGE_MLP);
+        edge_mlp(e, P, xm[cur], src, etype, rl, K, ly.x2h.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st, ew_x, fused_logits(e) ? q : nullptr, nullptr,
+                 nullptr, fuse_agg ? 1 : 0, fl);
+        edge_mlp(e, P, xm[cur], src, etype, rl, K, ly.x2h.v, ly.offsets, ly.coeff, e->vbuf.as<float>(), st, ew_x, nullptr,
+                 fuse_agg ? e->kbuf.as<float>() : nullptr, fuse_agg ? agg_target : nullptr, 0, fl);
+      }
+      if (!fuse_agg) {
+        Prof pr(e, st, EV_AGG_H);
+        if (fused_logits(e))
+          td_launch_aggregate_h_logits(e->kbuf.as<float>(), e->vbuf.as<float>(), ew_x, src, e->out_fc ? agg_target : h, agg_target, N, K,
+                                       e->ew_mode == 2 ? ly.x2h.ew_w : nullptr, ly.x2h.ew_b, st);
+        else td_launch_aggregate_h(e->kbuf.as<float>(), e->vbuf.as<float>(), e->e_w.as<float>(), src, q, h, h, N, K, st);
+      }
+      e->launches += fuse_agg ? 4 : 5;
+      if (e->out_fc) {               // h <- h + node_output([aggregate | h])   (reference models/uni_transformer.py:80-83); P is free here
+        float* t1 = P;
+        float* t2 = P + (size_t)N * TD_H;
+        TdMlp m1 = ly.x2h.out;
+        m1.b2 = e->zeros128;
+        td_launch_rows_tc(1, agg_target, TD_H, 0, N, m1, ly.x2h.out_wa_img, e->mlp_mode, t1, TD_H, 1, nullptr, nullptr, e->sm_count, st);
+        m1.b2 = ly.x2h.out_b1;
+        td_launch_rows_tc(1, h, TD_H, 0, N, m1, ly.x2h.out_wb_img, e->mlp_mode, t2, TD_H, 1, nullptr, nullptr, e->sm_count, st);
+        td_launch_add_rows(t1, t2, t1, (long long)N * TD_H, st);
+        td_launch_rows_tc(2, t1, TD_H, 0, N, ly.x2h.out, ly.x2h.out.w2_img, e->mlp_mode, t2, TD_H, 1, nullptr, nullptr, e->sm_count, st);
+        td_launch_add_rows(h, t2, h, (long long)N * TD_H, st);
+        e->launches += 6;
+      }
+      if (fl >= 0) {                 // clean protein rows: cached ligand-free features of this layer
+        td_launch_restore_clean(e->dirty.as<unsigned char>() + (size_t)fl * N, xm_blk, e->h_free.as<float>() + (size_t)fl * N * TD_H, N, h, st);
+        e->launches += 1;
+      }
+      if (free_build) {
+        cudaMemcpyAsync(e->h_free.as<float>() + l * (size_t)N * TD_H, h, (size_t)N * TD_H * 4, cudaMemcpyDeviceToDevice, st);
+        continue;
+      }
+      if (fix_x || Nl == 0) continue;     // h2x only moves ligand atoms; with fix_x its result is discarded (:204-206)
+      // ---- h2x: x_lig <- x_lig + mean_heads sum_e alpha * v * e_w * (x_dst - x_src), destinations = ligand atoms only
+      {
+        const bool rel = fused_logits(e) && !e->env_no_restrict;      // h2x only reads P / q of ligand atoms and their neighbours
+        node_side(e, h, N, ly.h2x, P, q, st, rel ? e->rel_list.as<int>() : nullptr, rel ? e->n_rel.as<int>() : nullptr);
+      }
+      {
+        Prof pr(e, st, EV_EDGE_MLP);
+        edge_mlp(e, P, xm[cur], src, etype, ROWS_LIGAND, K, ly.h2x.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st, ew_h, fused_logits(e) ? q : nullptr);
+        edge_mlp(e, P, xm[cur], src, etype, ROWS_LIGAND, K, ly.h2x.v, ly.offsets, ly.coeff, e->v16.as<float>(), st, ew_h);
+      }
+      {
+        Prof pr(e, st, EV_AGG_X);
+        if (fused_logits(e))
+          td_launch_aggregate_x_logits(e->kbuf.as<float>(), e->v16.as<float>(), ew_h, src, xm[cur], e->lig_node.as<int>(), xm[cur ^ 1], Nl, K, st);
+        else
+          td_launch_aggregate_x(e->kbuf.as<float>(), e->v16.as<float>(), e->e_w.as<float>(), src, q, xm[cur], e->lig_node.as<int>(), xm[cur ^ 1], Nl, K, st);
+      }
+      e->launches += 5;
+      cur ^= 1;
     }
-    {
-      Prof pr(e, st, EV_EDGE_MLP);
-      edge_mlp(e, P, xm[cur], src, etype, ROWS_LIGAND, K, ly.h2x.k, ly.offsets, ly.coeff, e->kbuf.as<float>(), st, fused_logits(e) ? q : nullptr);
-      edge_mlp(e, P, xm[cur], src, etype, ROWS_LIGAND, K, ly.h2x.v, ly.offsets, ly.coeff, e->v16.as<float>(), st);
-    }
-    {
-      Prof pr(e, st, EV_AGG_X);
-      if (fused_logits(e))
-        td_launch_aggregate_x_logits(e->kbuf.as<float>(), e->v16.as<float>(), e->e_w.as<float>(), src, xm[cur], e->lig_node.as<int>(), xm[cur ^ 1], Nl, K, st);
-      else
-        td_launch_aggregate_x(e->kbuf.as<float>(), e->v16.as<float>(), e->e_w.as<float>(), src, q, xm[cur], e->lig_node.as<int>(), xm[cur ^ 1], Nl, K, st);
-    }
-    e->launches += 5;
-    cur ^= 1;
   }
+  if (free_build) return;
   td_launch_head(h, e->lig_node.as<int>(), Nl, e->hd_w1t, e->hd_b1, e->hd_w2, e->hd_b2, e->cfg.num_classes, e->logits.as<float>(), st);
   e->launches += 1;
   e->final_buf = cur;
@@ -710,6 +876,15 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x) {
   e->have_prev = true;
 }
 }  // namespace
+
+extern "C" int tdiff_set_time(tdiff_engine* e, const float* d_time_norm, void* stream) {
+  if (!e || !e->bound) return set_err(TDIFF_ESTATE, "set_time before bind_batch");
+  if (!e->time_emb) return TDIFF_OK;           // no time embedding in this model: nothing to set
+  if (!d_time_norm) return set_err(TDIFF_EINVAL, "null time array");
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpyAsync(e->time_norm.p, d_time_norm, (size_t)e->B * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return TDIFF_OK;
+}
 
 extern "C" int tdiff_forward(tdiff_engine* e, float* d_pred_pos, float* d_pred_logits, float* d_final_h, int fix_x, void* stream) {
   if (!e || !e->bound || !e->has_ligand) return set_err(TDIFF_ESTATE, "forward needs bind_batch + set_ligand first");
@@ -773,7 +948,30 @@ extern "C" int tdiff_get_node_pos(tdiff_engine* e, float* d_x, void* stream) {
 
 // ---------------------------------------------------------------------------------------------- sampling loop
 namespace {
+// Ligand-free features of the first `free_depth` x2h layers (once per bound batch): the ligand atoms are parked far away so that no
+// protein atom has one among its neighbours, the ordinary kernels run, and the protein rows are exactly what a clean node gets later.
+void build_free_cache(tdiff_engine* e, cudaStream_t st) {
+  const size_t Nl = (size_t)e->Nl;
+  char* sv = e->lig_save.as<char>();
+  cudaMemcpyAsync(sv, e->lig_pos.p, Nl * 16, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(sv + Nl * 16, e->lig_v.p, Nl * 4, cudaMemcpyDeviceToDevice, st);
+  td_launch_park_ligand(e->lig_pos.as<float4>(), e->lig_v.as<int>(), e->Nl, st);
+  const bool had_prev = e->have_prev;
+  e->have_prev = false;
+  run_forward(e, st, 1, e->free_depth);
+  e->have_prev = false;               // src_prev now holds the parked graph: the next forward re-evaluates every edge constant
+  (void)had_prev;
+  cudaMemcpyAsync(e->lig_pos.p, sv, Nl * 16, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(e->lig_v.p, sv + Nl * 16, Nl * 4, cudaMemcpyDeviceToDevice, st);
+  e->launches += 1;
+  e->free_ready = true;
+}
+
 void run_step(tdiff_engine* e, cudaStream_t st, const TdStepArgs& base) {
+  if (e->time_emb) {               // every graph is at time step t_start - step (reference models/molopt_score_model.py:651)
+    td_launch_set_time(base.step, base.t_start, e->cfg.num_timesteps, e->B, e->time_norm.as<float>(), st);
+    e->launches += 1;
+  }
   e->restrict_last = true;
   run_forward(e, st, 0);
   e->restrict_last = false;
@@ -806,6 +1004,7 @@ extern "C" int tdiff_sample(tdiff_engine* e, int num_steps, const float* d_pos_n
   A.lig_pos = e->lig_pos.as<float4>(); A.lig_v = e->lig_v.as<int>();
   A.pos_traj = d_pos_traj; A.v_traj = (long long*)d_v_traj; A.v0_traj = d_v0_traj; A.vt_traj = d_vt_traj;
   CK(cudaMemsetAsync(e->step.p, 0, sizeof(int), st));
+  if (e->free_depth > 0 && !e->free_ready) build_free_cache(e, st);
   const bool eager = e->profiling || e->env_no_graph;
   Prof* total = new Prof(e, st, EV_TOTAL);
   // first step eagerly (module loading, shared-memory attributes), the rest replayed from one captured graph

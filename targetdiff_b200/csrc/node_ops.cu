@@ -34,6 +34,7 @@ void td_launch_protein_embed(const float* feat, int n_protein, int fdim, const f
 // h <- [protein: cached embedding | ligand: W_l[:, v] + b_l, indicator 1]; one float4 per thread.
 __global__ void init_h_kernel(const float* __restrict__ h0, const float4* __restrict__ xm, const int* __restrict__ lig_v,
                               const int* __restrict__ node_lig, const float* __restrict__ wl_t, const float* __restrict__ bl,
+                              const float* __restrict__ w_time, const float* __restrict__ time_norm, const int* __restrict__ lig_graph,
                               int n_nodes, float* __restrict__ h) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n_nodes * (TD_H / 4)) return;
@@ -47,16 +48,42 @@ __global__ void init_h_kernel(const float* __restrict__ h0, const float4* __rest
     const float4 wv = *reinterpret_cast<const float4*>(wl_t + (size_t)v * TD_H + 4 * f4);
     const float4 bv = *reinterpret_cast<const float4*>(bl + 4 * f4);
     o.x = wv.x + bv.x; o.y = wv.y + bv.y; o.z = wv.z + bv.z; o.w = wv.w + bv.w;
+    if (w_time) {                                // time_emb_mode 'simple': extra input column time_step / T (models/molopt_score_model.py:319-324)
+      const float tn = time_norm[lig_graph[a]];
+      const float4 wt = *reinterpret_cast<const float4*>(w_time + 4 * f4);
+      o.x = fmaf(wt.x, tn, o.x); o.y = fmaf(wt.y, tn, o.y); o.z = fmaf(wt.z, tn, o.z); o.w = fmaf(wt.w, tn, o.w);
+    }
     if (f4 == TD_H / 4 - 1) o.w = 1.0f;          // node_indicator column
   }
   *reinterpret_cast<float4*>(h + (size_t)n * TD_H + 4 * f4) = o;
 }
 
 void td_launch_init_h(const float* h0, const float4* xm, const int* lig_v, const int* node_lig, const float* wl_t, const float* bl,
-                      int n_nodes, float* h, cudaStream_t st) {
+                      const float* w_time, const float* time_norm, const int* lig_graph, int n_nodes, float* h, cudaStream_t st) {
   if (n_nodes == 0) return;
   long long n = (long long)n_nodes * (TD_H / 4);
-  init_h_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(h0, xm, lig_v, node_lig, wl_t, bl, n_nodes, h);
+  init_h_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(h0, xm, lig_v, node_lig, wl_t, bl, w_time, time_norm, lig_graph, n_nodes, h);
+}
+
+// out = a + b (x2h_out_fc glue: sum of the two halves of the node_output first Linear; residual add)
+__global__ void add_rows_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 x = a[i], y = b[i];
+  out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+}
+void td_launch_add_rows(const float* a, const float* b, float* out, long long n_floats, cudaStream_t st) {
+  const long long n4 = n_floats / 4;
+  if (n4 > 0) add_rows_kernel<<<(int)((n4 + 255) / 256), 256, 0, st>>>((const float4*)a, (const float4*)b, (float4*)out, n4);
+}
+
+// sampling loop, time embedding: every graph is at time step t_start - *step  ->  time_norm = t / T (fp32 division like the reference)
+__global__ void set_time_kernel(const int* __restrict__ step, int t_start, int n_timesteps, int n_graphs, float* __restrict__ time_norm) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_graphs) time_norm[g] = (float)(t_start - *step) / (float)n_timesteps;
+}
+void td_launch_set_time(const int* step, int t_start, int n_timesteps, int n_graphs, float* time_norm, cudaStream_t st) {
+  if (n_graphs > 0) set_time_kernel<<<(n_graphs + 255) / 256, 256, 0, st>>>(step, t_start, n_timesteps, n_graphs, time_norm);
 }
 
 // ---------------------------------------------------------------------------------------------- node projection

@@ -208,6 +208,17 @@ void td_launch_get_ligand(const float4* lig_pos, const int* lig_v, const int* li
   if (n > 0) get_ligand_kernel<<<(n + 255) / 256, 256, 0, st>>>(lig_pos, lig_v, lig_graph, offset, add_offset, n, pos, v);
 }
 
+// ligand atoms parked far from every pocket (distinct points; ligand-free cache construction, engine.cu)
+__global__ void park_ligand_kernel(float4* __restrict__ lig_pos, int* __restrict__ lig_v, int n) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  lig_pos[a] = make_float4(1.0e6f + 64.0f * (float)(a & 4095), 1.0e6f + 64.0f * (float)((a >> 12) & 4095), 1.0e6f, 1.0f);
+  lig_v[a] = 0;
+}
+void td_launch_park_ligand(float4* lig_pos, int* lig_v, int n, cudaStream_t st) {
+  if (n > 0) park_ligand_kernel<<<(n + 255) / 256, 256, 0, st>>>(lig_pos, lig_v, n);
+}
+
 // ligand rows of the node array <- ligand state (start of every forward)
 __global__ void scatter_ligand_pos_kernel(const float4* __restrict__ lig_pos, const int* __restrict__ lig_node, int n, float4* __restrict__ xm) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;

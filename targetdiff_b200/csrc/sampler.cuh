@@ -31,6 +31,7 @@ void td_launch_step_epilogue(const TdStepArgs& A, cudaStream_t st);
 void td_launch_segment_mean3(const float* pos, const int* seg_ptr, int n_seg, float4* out, cudaStream_t st);
 void td_launch_place_protein(const float* pos, const int* prot_node, const int* prot_graph, const float4* offset, int n, float4* xm0,
                              float4* xm1, cudaStream_t st);
+void td_launch_park_ligand(float4* lig_pos, int* lig_v, int n, cudaStream_t st);
 void td_launch_set_ligand(const float* pos, const long long* v, const int* lig_graph, const float4* offset, int apply_center, int n,
                           int n_classes, float4* lig_pos, int* lig_v, int* err, cudaStream_t st);
 void td_launch_get_ligand(const float4* lig_pos, const int* lig_v, const int* lig_graph, const float4* offset, int add_offset, int n,

@@ -33,11 +33,29 @@ struct TdMlp {
                                      // (class 0 = protein destination: types 3 | 1, class 1 = ligand destination: types 2 | 0)
 };
 
+// ew_net_type 'r': per-layer gate parameters of both sub-layers and the per-slot outputs (all NULL when unused)
+struct TdEwR {
+  const float* w_x2h;      // [80] Linear(r_feat -> 1) of the x2h sub-layer (type-major: 20 type + j)
+  const float* w_h2x;      // [80] same for h2x
+  float b_x2h, b_h2x;
+  const float* offsets;    // [20] gaussian centres of the layer
+  float coeff;
+  float* out_x2h;          // [N*k] gates
+  float* out_h2x;
+};
+
 struct TdSubLayer {       // x2h or h2x
   const float* wn_t;      // [128][TD_NPROJ] node projection weights (transposed)
   const float* bn;        // [TD_NPROJ] bias (non-zero only in the q_pre block)
   const unsigned char* wn_img;   // the same weights as 5 UMMA images of [128 x 128] (3 bf16 pieces each) for the tensor-core path
   TdMlp k, v, q;          // q.tab unused
+  const float* ew_w;      // ew_net_type 'r': [80], 'm' (x2h only): [128]; else NULL
+  float ew_b;
+  // x2h_out_fc: node_output MLP(256 -> 128 -> 128) on [aggregate | h] (reference models/uni_transformer.py:39-40,80-81)
+  const unsigned char* out_wa_img;   // first Linear, columns that multiply the aggregate
+  const unsigned char* out_wb_img;   // first Linear, columns that multiply h
+  const float* out_b1;               // [128]
+  TdMlp out;                         // LayerNorm affine + second Linear (ln_g, ln_b, b2, w2_img)
 };
 
 struct TdLayer {
@@ -130,18 +148,23 @@ void td_launch_knn_update(const float4* xm, const int* node_ptr, const int* prot
                           const unsigned long long* cache, int* src, cudaStream_t st);
 void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int have_prev, int n_nodes, int k, const float* offsets, float coeff,
                           const float* w1t, const float* b1, const float* ln_g, const float* ln_b, const float* w2, float b2,
-                          unsigned char* etype, float* e_w, unsigned char* rel_flag, int* work_list, int* n_work, cudaStream_t st);
+                          unsigned char* etype, float* e_w, unsigned char* rel_flag, unsigned char* touch_flag, int* work_list, int* n_work,
+                          int gate_mode, cudaStream_t st);
+void td_launch_dirty_propagate(const unsigned char* in, const int* src, int n_nodes, int k, unsigned char* out, cudaStream_t st);
+void td_launch_restore_clean(const unsigned char* dirty, const float4* xm, const float* h_free, int n_nodes, float* h, cudaStream_t st);
 void td_launch_rel_rows(const unsigned char* rel_flag, const float4* xm, int n_nodes, const int* lig_rows, int n_lig_rows, int pad, int* rel_rows,
                         int* rel_counts, cudaStream_t st);
 void td_launch_protein_embed(const float* feat, int n_protein, int fdim, const float* w, const float* b, const int* prot_node,
                              float* h0, cudaStream_t st);
 void td_launch_init_h(const float* h0, const float4* xm, const int* lig_v, const int* node_lig, const float* wl_t, const float* bl,
-                      int n_nodes, float* h, cudaStream_t st);
+                      const float* w_time, const float* time_norm, const int* lig_graph, int n_nodes, float* h, cudaStream_t st);
 void td_launch_node_proj(const float* h, int n_nodes, const float* wn_t, const float* bn, float* P, cudaStream_t st);
 void td_launch_node_q(const float* P, int n_nodes, TdMlp q, float* qout, cudaStream_t st);
 void td_launch_edge_mlp(const float* P, const float4* xm, const int* src, const unsigned char* etype, const int* row_nodes,
                         long long n_rows, int k, TdMlp m, const float* offsets, float coeff, float* out, int sm_count, cudaStream_t st);
-void td_launch_edge_geom(const float4* xm, const int* src, int n_nodes, int k, float* dist, cudaStream_t st);
+void td_launch_edge_geom(const float4* xm, const int* src, const unsigned char* etype, int n_nodes, int k, float* dist, const TdEwR& ew, cudaStream_t st);
+void td_launch_add_rows(const float* a, const float* b, float* out, long long n_floats, cudaStream_t st);
+void td_launch_set_time(const int* step, int t_start, int n_timesteps, int n_graphs, float* time_norm, cudaStream_t st);
 void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, const unsigned char* etype, const float* dist,
                            const int* row_nodes, long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
                            float* out, int sm_count, cudaStream_t st);
@@ -157,7 +180,7 @@ void td_launch_aggregate_h(const float* kbuf, const float* vbuf, const float* e_
 void td_launch_aggregate_x(const float* kbuf, const float* v16, const float* e_w, const int* src, const float* q, const float4* xm_in,
                            const int* row_nodes, float4* xm_out, int n_rows, int k, cudaStream_t st);
 void td_launch_aggregate_h_logits(const float* logits, const float* vbuf, const float* e_w, const int* src, const float* h_in, float* h_out,
-                                  int n_nodes, int k, cudaStream_t st);
+                                  int n_nodes, int k, const float* ewm_w, float ewm_b, cudaStream_t st);
 void td_launch_aggregate_x_logits(const float* logits, const float* v16, const float* e_w, const int* src, const float4* xm_in,
                                   const int* row_nodes, float4* xm_out, int n_rows, int k, cudaStream_t st);
 void td_launch_head(const float* h, const int* lig_node, int n_lig, const float* w1t, const float* b1, const float* w2, const float* b2,

@@ -107,34 +107,50 @@ class _Offsets(nn.Module):
 
 
 class _X2H(nn.Module):
-    def __init__(self, H, kv_dim):
+    """parameter holder of BaseX2HAttLayer (reference models/uni_transformer.py:11-40; same module order = same state_dict order)"""
+
+    def __init__(self, H, kv_dim, r_dim, ew_net_type, out_fc):
         super().__init__()
         self.hk_func, self.hv_func, self.hq_func = MLP(kv_dim, H, H), MLP(kv_dim, H, H), MLP(H, H, H)
+        if ew_net_type == 'r':
+            self.ew_net = nn.Sequential(nn.Linear(r_dim, 1), _Act())
+        elif ew_net_type == 'm':
+            self.ew_net = nn.Sequential(nn.Linear(H, 1), _Act())
+        if out_fc:
+            self.node_output = MLP(2 * H, H, H)
 
 
 class _H2X(nn.Module):
-    def __init__(self, H, kv_dim, n_heads):
+    """parameter holder of BaseH2XAttLayer (reference models/uni_transformer.py:86-106)"""
+
+    def __init__(self, H, kv_dim, n_heads, r_dim, ew_net_type):
         super().__init__()
         self.xk_func, self.xv_func, self.xq_func = MLP(kv_dim, H, H), MLP(kv_dim, n_heads, H), MLP(H, H, H)
+        if ew_net_type == 'r':
+            self.ew_net = nn.Sequential(nn.Linear(r_dim, 1), _Act())
 
 
 class _AttLayer(nn.Module):
-    def __init__(self, H, n_heads, kv_dim, num_x2h, num_h2x):
+    def __init__(self, H, n_heads, kv_dim, r_dim, num_x2h, num_h2x, ew_net_type, out_fc):
         super().__init__()
         self.distance_expansion = _Offsets()
-        self.x2h_layers = nn.ModuleList([_X2H(H, kv_dim) for _ in range(num_x2h)])
-        self.h2x_layers = nn.ModuleList([_H2X(H, kv_dim, n_heads) for _ in range(num_h2x)])
+        self.x2h_layers = nn.ModuleList([_X2H(H, kv_dim, r_dim, ew_net_type, out_fc) for _ in range(num_x2h)])
+        self.h2x_layers = nn.ModuleList([_H2X(H, kv_dim, n_heads, r_dim, ew_net_type) for _ in range(num_h2x)])
 
 
 class _RefineNet(nn.Module):
     def __init__(self, cfg):
         super().__init__()
         H = cfg.hidden_dim
-        kv_dim = 2 * H + cfg.edge_feat_dim + 4 * cfg.num_r_gaussian
+        r_dim = 4 * cfg.num_r_gaussian
+        kv_dim = 2 * H + cfg.edge_feat_dim + r_dim
+        ew, fc = cfg.ew_net_type, bool(cfg.x2h_out_fc)
         self.distance_expansion = _Offsets()
-        self.edge_pred_layer = MLP(cfg.num_r_gaussian, 1, H)
-        self.init_h_emb_layer = _AttLayer(H, cfg.n_heads, kv_dim, 1, 0)      # never evaluated; present for strict loading
-        self.base_block = nn.ModuleList([_AttLayer(H, cfg.n_heads, kv_dim, cfg.num_x2h, cfg.num_h2x) for _ in range(cfg.num_layers)])
+        if ew == 'global':
+            self.edge_pred_layer = MLP(cfg.num_r_gaussian, 1, H)
+        self.init_h_emb_layer = _AttLayer(H, cfg.n_heads, kv_dim, r_dim, 1, 0, ew, fc)      # never evaluated; present for strict loading
+        self.base_block = nn.ModuleList([_AttLayer(H, cfg.n_heads, kv_dim, r_dim, cfg.num_x2h, cfg.num_h2x, ew, fc)
+                                         for _ in range(cfg.num_layers)])
 
 
 def log_sample_categorical(logits):
@@ -182,7 +198,8 @@ class ScorePosNet3D(nn.Module):
         self.center_pos_mode = config.center_pos_mode
         self.time_emb_dim = config.time_emb_dim
         self.time_emb_mode = config.time_emb_mode
-        self.ligand_atom_emb = nn.Linear(ligand_atom_feature_dim, emb_dim)
+        # time_emb_mode 'simple' appends time_step / T to the ligand one-hot (reference :289-291,319-324)
+        self.ligand_atom_emb = nn.Linear(ligand_atom_feature_dim + (1 if self.time_emb_dim > 0 else 0), emb_dim)
         self.refine_net_type = config.model_type
         self.refine_net = _RefineNet(config)
         self.v_inference = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), _Act(), nn.Linear(self.hidden_dim, ligand_atom_feature_dim))
@@ -232,7 +249,9 @@ class ScorePosNet3D(nn.Module):
             entries[i].name, entries[i].data, entries[i].numel = name, v.data_ptr(), v.numel()
         cfg = _lib.tdiff_config(self.hidden_dim, self.config.n_heads, self.config.num_layers, self.config.knn, self.config.num_r_gaussian,
                                 self.num_classes, self.protein_atom_feature_dim, self.num_timesteps,
-                                {'C0': 0, 'noise': 1}[self.model_mean_type])
+                                {'C0': 0, 'noise': 1}[self.model_mean_type], int(self.config.num_blocks),
+                                {'global': 0, 'r': 1, 'm': 2, 'none': 3}[self.config.ew_net_type], int(bool(self.config.x2h_out_fc)),
+                                1 if self.time_emb_dim > 0 else 0)
         out = ctypes.c_void_p()
         _lib.check(lib.tdiff_create(ctypes.byref(cfg), entries, len(sd), index, ctypes.byref(out)))
         self._engine, self._engine_device, self._bound_key = out, index, None
@@ -263,7 +282,7 @@ class ScorePosNet3D(nn.Module):
     @torch.no_grad()
     def forward(self, protein_pos, protein_v, batch_protein, init_ligand_pos, init_ligand_v, batch_ligand,
                 time_step=None, return_all=False, fix_x=False, return_edge_weight=False):
-        """One network evaluation (reference models/molopt_score_model.py:313-368; time_emb_dim=0 so `time_step` is unused).
+        """One network evaluation (reference models/molopt_score_model.py:313-368; `time_step` [B] is only read with time_emb_dim > 0).
         Returns {'pred_ligand_pos','pred_ligand_v','final_h','final_ligand_h'}; additionally 'edge_index' (int64 [2,E]) and, with
         `return_edge_weight`, 'edge_weight' [E]: the global edge gate e_w in edge_index order (models/uni_transformer.py:312-316)."""
         if return_all:
@@ -278,6 +297,13 @@ class ScorePosNet3D(nn.Module):
         if lpos.shape[0] != Nl or lv.shape[0] != Nl:
             raise ValueError('ligand arrays disagree with batch_ligand')
         _lib.check(lib.tdiff_set_ligand(eng, _ptr(lpos), _ptr(lv), 0, st))
+        if self.time_emb_dim > 0:           # (time_step / T) per graph, fp32 like the reference's true division (:322)
+            if time_step is None:
+                raise ValueError('time_step is required when time_emb_dim > 0')
+            tn = (time_step.to(dev) / self.num_timesteps).to(torch.float32).contiguous()
+            if tn.numel() != B:
+                raise ValueError('time_step must have one entry per graph')
+            _lib.check(lib.tdiff_set_time(eng, _ptr(tn), st))
         pred_pos = torch.empty(Nl, 3, device=dev)
         logits = torch.empty(Nl, self.num_classes, device=dev)
         final_h = torch.empty(Np + Nl, self.hidden_dim, device=dev)

@@ -192,6 +192,27 @@ def test_relevant_node_restriction_is_exact(monkeypatch):
     assert torch.equal(torch.stack(res[0]['pos_traj']), torch.stack(res[1]['pos_traj']))
 
 
+@pytest.mark.parametrize('n_protein,sizes', [(250, [20, 7, 33, 1, 25, 12]), (120, [9, 30])])
+def test_ligand_free_cache_is_exact(monkeypatch, n_protein, sizes):
+    """The first x2h layers only visit destinations whose features can differ from their ligand-free values (nodes with a ligand
+    atom among their neighbours, then layer by layer the nodes fed by such nodes); the others are restored from features computed
+    once per bound batch (protein atoms never move, reference models/uni_transformer.py:205-206, and their embedding is
+    step-invariant, models/molopt_score_model.py:333).  Rows are independent, so the chain must be bit-identical to the one
+    computed without the cache (TDIFF_FREE_DEPTH=0), for any cache depth."""
+    b = synth.make_batch(6, len(sizes), n_protein=n_protein, ligand_sizes=sizes)
+    S = 10
+    pn, vu = synth.make_tape(11, S, int(b['init_ligand_pos'].shape[0]))
+    res = []
+    for depth in ('0', '1', '2', '4'):
+        monkeypatch.setenv('TDIFF_FREE_DEPTH', depth)
+        model, _ = _model(3)
+        res.append(model.sample_diffusion(*_args(b), num_steps=S, center_pos_mode='protein', noise_tape=(pn, vu)))
+    for r in res[1:]:
+        assert torch.equal(res[0]['pos'], r['pos']) and torch.equal(res[0]['v'], r['v'])
+        assert torch.equal(torch.stack(res[0]['v0_traj']), torch.stack(r['v0_traj']))
+        assert torch.equal(torch.stack(res[0]['pos_traj']), torch.stack(r['pos_traj']))
+
+
 def test_likelihood_estimation_vs_oracle_and_golden():
     """SURVEY 8(f) n3 (reference models/molopt_score_model.py:565-617): the network call runs on libtdiff.so; compared with the CPU
     oracle on the same noise and with the vectors the reference itself wrote (tests/golden/likelihood.npz)."""

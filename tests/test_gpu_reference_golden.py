@@ -212,3 +212,35 @@ def test_sample_host_odd_sizes_all_trajectories():
     assert torch.equal(pos_traj, r['pos_traj']) and torch.equal(v_traj, r['v_traj'])
     assert torch.equal(v0_traj, r['v0_traj']) and torch.equal(vt_traj, r['vt_traj'])
     assert torch.equal(out_pos, r['pos'].cpu()) and torch.equal(out_v, r['v'].cpu())
+
+
+OPTION_CONFIGS = [{'num_blocks': 2}, {'ew_net_type': 'r'}, {'ew_net_type': 'm'}, {'ew_net_type': 'none'}, {'x2h_out_fc': True},
+                  {'time_emb_dim': 1, 'time_emb_mode': 'simple'}, {'num_blocks': 2, 'ew_net_type': 'r', 'x2h_out_fc': True, 'time_emb_dim': 1}]
+
+
+@pytest.mark.parametrize('cfgd', OPTION_CONFIGS, ids=lambda c: ','.join('%s=%s' % kv for kv in c.items()))
+def test_backbone_options_vs_oracle(cfgd):
+    """SURVEY 8(f) n2 on the engine: re-built k-NN graph per block (reference models/uni_transformer.py:306-307), per-sub-layer 'r' /
+    value-driven 'm' / absent edge gates (:58-66,121-129), node_output MLP (:39-40,80-81), time embedding 'simple'
+    (models/molopt_score_model.py:319-324): forward and a 6-step chain against the oracle (itself bit-exact against the reference,
+    tests/test_oracle_vs_reference.py::test_backbone_options_restatement_bit_exact)."""
+    torch.set_num_threads(16)
+    model, sd = _model(2, cfgd)
+    b = synth.make_batch(9, 3, n_protein=70, ligand_sizes=[12, 5, 9])
+    pp, lp, _ = restate.center_pos(b['protein_pos'], b['init_ligand_pos'], b['batch_protein'], b['batch_ligand'])
+    t = torch.tensor([999, 500, 3])
+    tr = {}
+    want = restate.forward(sd, cfgd, pp, b['protein_v'], b['batch_protein'], lp, b['init_ligand_v'], b['batch_ligand'], trace=tr, time_step=t)
+    out = model(pp.to(DEV), b['protein_v'].to(DEV), b['batch_protein'].to(DEV), lp.to(DEV), b['init_ligand_v'].to(DEV), b['batch_ligand'].to(DEV),
+                time_step=t.to(DEV))
+    assert torch.equal(out['edge_index'].cpu(), tr['block_edge_index'][-1])          # graph of the last block
+    torch.testing.assert_close(out['pred_ligand_pos'].cpu(), want['pred_ligand_pos'], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out['pred_ligand_v'].cpu(), want['pred_ligand_v'], rtol=0, atol=1e-3)
+    torch.testing.assert_close(out['final_h'].cpu(), want['final_h'], rtol=1e-4, atol=1e-4)
+    S = 6
+    pn, vu = synth.make_tape(4, S, len(b['batch_ligand']))
+    w = restate.sample_diffusion(sd, cfgd, *_args(b, 'cpu'), pn, vu, num_steps=S)
+    got = model.sample_diffusion(*_args(b), num_steps=S, center_pos_mode='protein', noise_tape=(pn, vu))
+    assert torch.equal(torch.stack(got['v_traj']), torch.stack(w['v_traj']))
+    torch.testing.assert_close(torch.stack(got['pos_traj']), torch.stack(w['pos_traj']), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(torch.stack(got['v0_traj']), torch.stack(w['v0_traj']), rtol=0, atol=1e-3)

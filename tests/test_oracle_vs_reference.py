@@ -127,3 +127,58 @@ def test_sampling_chain_noise_mean_type_bit_exact():
     assert torch.equal(want['pos'], got['pos']) and torch.equal(want['v'], got['v'])
     for k in ('pos_traj', 'v_traj', 'v0_traj', 'vt_traj'):
         assert all(torch.equal(a, c) for a, c in zip(want[k], got[k])), k
+
+
+OPTION_CONFIGS = [{'num_blocks': 2}, {'ew_net_type': 'r'}, {'ew_net_type': 'm'}, {'ew_net_type': 'none'}, {'x2h_out_fc': True},
+                  {'time_emb_dim': 1, 'time_emb_mode': 'simple'}, {'num_blocks': 2, 'ew_net_type': 'r', 'x2h_out_fc': True, 'time_emb_dim': 1}]
+
+
+@pytest.mark.parametrize('cfgd', OPTION_CONFIGS, ids=lambda c: ','.join('%s=%s' % kv for kv in c.items()))
+def test_backbone_options_restatement_bit_exact(cfgd):
+    """num_blocks > 1, ew_net_type r / m / none, x2h_out_fc, time_emb_mode 'simple' -- state_dict layout (key order and
+    shapes) and a 3-step sampling chain of the restatement against the unmodified reference, bit for bit."""
+    ref = refload.import_reference()
+    cfg = refload.default_model_config()
+    cfg.update(cfgd)
+    model = ref.ScorePosNet3D(cfg, synth.PROTEIN_FEATURE_DIM, synth.LIGAND_NUM_CLASSES).eval()
+    sd = synth.make_state_dict(0, cfgd, schedules=restate.make_schedules(cfgd))
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.load_state_dict(sd, strict=True)
+    b = synth.make_batch(3, 2, n_protein=60, ligand_sizes=[9, 7])
+    S = 3
+    pn, vu = synth.make_tape(5, S, 16)
+    args = (b['protein_pos'], b['protein_v'], b['batch_protein'], b['init_ligand_pos'], b['init_ligand_v'], b['batch_ligand'])
+    with torch.no_grad(), refload.noise_tape(pn, vu):
+        r = model.sample_diffusion(*args, num_steps=S, center_pos_mode='protein')
+    w = restate.sample_diffusion(sd, cfgd, *args, pn, vu, num_steps=S)
+    assert torch.equal(r['pos'], w['pos']) and torch.equal(r['v'], w['v'])
+    for a, c in zip(r['v0_traj'] + r['vt_traj'] + r['pos_traj'], w['v0_traj'] + w['vt_traj'] + w['pos_traj']):
+        assert torch.equal(a, c)
+
+
+def test_sampling_driver_restatement_bit_exact():
+    """a1: oracle.restate.sample_diffusion_ligand against the UNMODIFIED reference driver (scripts/sample_diffusion.py:31-116, imported with
+    placeholders for rdkit / openbabel / lmdb) on the 1h36 pocket: same seeds -> the same prior sizes, positions, types and trajectories."""
+    import json
+    import os
+    import numpy as np
+    sd_mod, sfp = refload.import_reference_scripts()
+    import utils.misc as misc
+    import utils.transforms as trans
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    data = trans.FeaturizeProteinAtom()(sfp.pdb_to_pocket_data(os.path.join(root, 'tests', 'golden', '1h36_pocket10.pdb')))
+    ref = refload.import_reference()
+    sd = synth.make_state_dict(0, schedules=restate.make_schedules())
+    model = ref.ScorePosNet3D(refload.default_model_config(), synth.PROTEIN_FEATURE_DIM, synth.LIGAND_NUM_CLASSES).eval()
+    model.load_state_dict(sd, strict=True)
+    misc.seed_all(2021)
+    out = sd_mod.sample_diffusion_ligand(model, data, 3, batch_size=2, device='cpu', num_steps=2, center_pos_mode='protein', sample_num_atoms='prior')
+    prior = json.load(open(os.path.join(root, 'targetdiff_b200', 'data', 'atom_num_prior.json')))
+    misc.seed_all(2021)
+    out2 = restate.sample_diffusion_ligand(sd, None, data.protein_pos, data.protein_atom_feature, 3, prior, batch_size=2, num_steps=2)
+    for a, b in zip(out[:6], out2[:6]):
+        assert len(a) == len(b) == 3 and all(np.array_equal(x, y) for x, y in zip(a, b))
+    # the product's PDB ingest gives the reference's tensors
+    from targetdiff_b200.pocket import pdb_to_pocket_data
+    mine = pdb_to_pocket_data(os.path.join(root, 'tests', 'golden', '1h36_pocket10.pdb'))
+    assert torch.equal(mine.protein_pos, data.protein_pos) and torch.equal(mine.protein_atom_feature, data.protein_atom_feature)

@@ -15,6 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -45,7 +46,7 @@ def knn_agreement(b, pos_traj_a, pos_traj_b, k):
 
 
 def run(name, mode):
-    from tests.test_gpu_reference_golden import _args, _model, chain_divergence
+    from test_gpu_reference_golden import _args, _model, chain_divergence
     case = LONG_CASES[name]
     path = os.path.join(GOLDEN, name + '.npz')
     if not os.path.exists(path):

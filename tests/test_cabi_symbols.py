@@ -56,12 +56,21 @@ def test_state_dict_layout_and_unsupported_configs():
     sched = restate.make_schedules()
     assert all(torch.equal(sd[k], sched[k]) for k in synth.SCHEDULE_KEYS)
     m.load_state_dict(synth.make_state_dict(0, schedules=sched), strict=True)
-    for bad in ({'cutoff_mode': 'radius'}, {'model_type': 'egnn'}, {'ew_net_type': 'r'}, {'num_blocks': 2}, {'time_emb_dim': 8},
-                {'x2h_out_fc': True}, {'hidden_dim': 256}):
+    for bad in ({'cutoff_mode': 'radius'}, {'cutoff_mode': 'hybrid'}, {'model_type': 'egnn'}, {'time_emb_dim': 8, 'time_emb_mode': 'sin'},
+                {'num_blocks': 0}, {'hidden_dim': 256}, {'ew_net_type': 'x'}):
         c = default_model_config()
         c.update(bad)
         with pytest.raises(NotImplementedError):
             ScorePosNet3D(c, 27, 13)
+    # the backbone options of SURVEY 8(f) n2 are accepted and give the reference's state_dict layout (key order and shapes)
+    for opt in ({'num_blocks': 2}, {'ew_net_type': 'r'}, {'ew_net_type': 'm'}, {'ew_net_type': 'none'}, {'x2h_out_fc': True},
+                {'time_emb_dim': 1, 'time_emb_mode': 'simple'}):
+        c = default_model_config()
+        c.update(opt)
+        m = ScorePosNet3D(c, 27, 13)
+        spec = synth.state_dict_spec(opt)
+        assert list(m.state_dict().keys()) == [k for k, _, _ in spec], opt
+        assert all(tuple(m.state_dict()[k].shape) == tuple(s) for k, s, _ in spec), opt
 
 
 def test_config_struct_matches_header():
@@ -69,7 +78,7 @@ def test_config_struct_matches_header():
     from targetdiff_b200 import _lib
     src = open(os.path.join(ROOT, 'include', 'tdiff.h')).read()
     body = src[src.index('typedef struct tdiff_config {'):src.index('} tdiff_config;')]
-    fields = re.findall(r'^\s*int32_t\s+([a-z_]+)(\[(\d+)\])?;', body, flags=re.M)
+    fields = re.findall(r'^\s*int32_t\s+([a-z0-9_]+)(\[(\d+)\])?;', body, flags=re.M)
     names = [f[0] for f in fields]
     words = sum(int(f[2]) if f[2] else 1 for f in fields)
     assert names == [n for n, _ in _lib.tdiff_config._fields_]

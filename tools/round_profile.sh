@@ -15,9 +15,11 @@ for w in $what; do
     ncu)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv python tools/eager_steps.py 3 > gpurun_out/${tag}_launches.log 2>&1
       python tools/launch_shares.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_launch_shares.csv; head -14 gpurun_out/${tag}_launch_shares.csv
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:edge_mlp_v4_kernel -s 6 -c 2 -o gpurun_out/${tag}_v4 python tools/eager_steps.py 2 > gpurun_out/${tag}_ncu.log 2>&1
+      # the two big launches of a middle layer of the second step: x2h key (softmax epilogue) and x2h value (+ fused aggregation)
+      TDIFF_FREE_DEPTH=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:edge_mlp_v4_kernel -s 52 -c 2 -o gpurun_out/${tag}_v4 python tools/eager_steps.py 2 > gpurun_out/${tag}_ncu.log 2>&1
       ncu -i gpurun_out/${tag}_v4.ncu-rep --page raw --csv > gpurun_out/${tag}_v4_raw.csv 2>/dev/null
-      ncu -i gpurun_out/${tag}_v4.ncu-rep --page source --csv > gpurun_out/${tag}_v4_source.csv 2>/dev/null ;;
+      ncu -i gpurun_out/${tag}_v4.ncu-rep --page source --csv --print-source sass > gpurun_out/${tag}_v4_source.csv 2>/dev/null
+      ncu -i gpurun_out/${tag}_v4.ncu-rep --page source --csv --print-source cuda > gpurun_out/${tag}_v4_source_cuda.csv 2>/dev/null ;;
     audit) timeout 900 python tools/precision_audit.py --out gpurun_out/${tag}_precision_audit.json > gpurun_out/${tag}_audit.log 2>&1; tail -8 gpurun_out/${tag}_audit.log ;;
   esac
 done

@@ -159,6 +159,15 @@ TDIFF_API int tdiff_attn_aggregate_x(const float* d_k, const float* d_v16, const
 /* scatter_mean(src [M,3], index [M] sorted, dim=0) given per-segment counts (models/molopt_score_model.py:115). */
 TDIFF_API int tdiff_scatter_mean3(const float* d_src, const int32_t* h_counts, int n_segments, float* d_out, void* stream);
 
+/* Bond-count stability screen of generated molecules (the step after the sampling path: utils/evaluation/analyze.py:106-143
+ * `check_stability`, called per molecule by scripts/evaluate_diffusion.py:78-84).  d_pos [n_atoms,3] fp32, d_atomic_num [n_atoms] int32
+ * (atomic numbers, utils/transforms.py `get_atomic_number_from_index`), h_counts [n_mol] atoms per molecule.  Outputs (device):
+ * d_nr_bonds [n_atoms] summed bond orders (may be NULL), d_stable_atoms [n_mol], d_mol_stable [n_mol] (1 = every atom stable).
+ * hs != 0 requires bonds == valence instead of 0 < bonds <= valence.  An atomic number outside the reference's table -> TDIFF_EINVAL
+ * (KeyError in the reference).  Synchronises the stream. */
+TDIFF_API int tdiff_check_stability(const float* d_pos, const int32_t* d_atomic_num, const int32_t* h_counts, int n_mol, int hs,
+                                    int32_t* d_nr_bonds, int32_t* d_stable_atoms, uint8_t* d_mol_stable, void* stream);
+
 /* ---- instrumentation ------------------------------------------------------------------------------------
  * Number of kernel launches issued by this engine since creation (graph replays count their nodes). */
 TDIFF_API int64_t tdiff_launch_count(tdiff_engine* e);

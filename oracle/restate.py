@@ -542,3 +542,47 @@ def likelihood_estimation(sd, cfg, protein_pos, protein_v, batch_protein, ligand
     nll_c = -(log_v0.exp() * log_model).sum(1)
     kl_v = _scatter_mean_rows(mask * nll_c + (1. - mask) * kl_c, batch_ligand, B)
     return kl_pos, kl_v
+
+
+# ----------------------------------------------------------------------------------------------
+# n4  stability screen of generated molecules                      utils/evaluation/analyze.py:6-44,90-143
+# ----------------------------------------------------------------------------------------------
+_ELEMENTS = ['H', 'C', 'N', 'O', 'F', 'P', 'S', 'Cl']
+_Z_TO_EL = {1: 0, 6: 1, 7: 2, 8: 3, 9: 4, 15: 5, 16: 6, 17: 7}                           # atom_encoder / atom_decoder, :6-7
+_BONDS1 = [[74, 109, 101, 96, 92, 144, 134, 127], [109, 154, 147, 143, 135, 184, 182, 177], [101, 147, 145, 140, 136, 177, 168, 175],
+           [96, 143, 140, 148, 142, 163, 151, 164], [92, 135, 136, 142, 142, 156, 158, 166], [144, 184, 177, 163, 156, 221, 210, 203],
+           [134, 182, 168, 151, 158, 210, 204, 207], [127, 177, 175, 164, 166, 203, 207, 199]]                                       # :10-18
+_BONDS2 = [[-1] * 8, [-1, 134, 129, 120, -1, -1, 160, -1], [-1, 129, 125, 121, -1, -1, -1, -1], [-1, 120, 121, 121, -1, 150, -1, -1],
+           [-1] * 8, [-1, -1, -1, 150, -1, -1, 186, -1], [-1, 160, -1, -1, -1, 186, -1, -1], [-1] * 8]                              # :21-29
+_BONDS3 = [[-1] * 8, [-1, 120, 116, 113, -1, -1, -1, -1], [-1, 116, 110, -1, -1, -1, -1, -1], [-1, 113, -1, -1, -1, -1, -1, -1],
+           [-1] * 8, [-1] * 8, [-1] * 8, [-1] * 8]                                                                                   # :31-39
+_ALLOWED = [1, 4, 3, 2, 1, 5, 4, 1]                                                                                                  # :44
+
+
+def get_bond_order(e1, e2, distance):
+    d = 100 * distance                                                                   # :91
+    if d < _BONDS1[e1][e2] + 10:                                                         # margin1, :94
+        if d < _BONDS2[e1][e2] + 5:                                                      # :95-96
+            if d < _BONDS3[e1][e2] + 3:                                                  # :97-98
+                return 3
+            return 2
+        return 1
+    return 0
+
+
+def check_stability(positions, atom_type, hs=False):
+    """analyze.py:106-143 -> (molecule_stable, nr_stable_atoms, n_atoms, nr_bonds); positions float64 [n,3], atom_type atomic numbers."""
+    positions = np.asarray(positions, dtype=np.float64)
+    n = len(positions)
+    nr_bonds = np.zeros(n, dtype='int')
+    for i in range(n):
+        for j in range(i + 1, n):
+            dist = np.sqrt(np.sum((positions[i] - positions[j]) ** 2))                   # :117-119
+            order = get_bond_order(_Z_TO_EL[int(atom_type[i])], _Z_TO_EL[int(atom_type[j])], dist)
+            nr_bonds[i] += order
+            nr_bonds[j] += order
+    stable = 0
+    for z, nb in zip(atom_type, nr_bonds):
+        a = _ALLOWED[_Z_TO_EL[int(z)]]
+        stable += int(a == nb) if hs else int(a >= nb > 0)                               # :130-133
+    return stable == n, stable, n, nr_bonds

@@ -1,5 +1,5 @@
 """Import-time placeholders for third-party packages the reference imports at module level but never CALLS on the sampling
-path (rdkit, openbabel, lmdb) -- TEST INFRASTRUCTURE ONLY.
+path (rdkit, openbabel, lmdb, matplotlib) -- TEST INFRASTRUCTURE ONLY.
 
 `install()` adds a meta-path finder that resolves `rdkit`, `rdkit.*`, `openbabel`, `openbabel.*`, `lmdb` to placeholder modules
 whose attributes are inert placeholder objects (hashable, callable -> placeholder, empty when measured or iterated), so that e.g. reference utils/data.py:3-12
@@ -11,7 +11,7 @@ import importlib.machinery
 import sys
 import types
 
-ABSENT_ROOTS = ('rdkit', 'openbabel', 'lmdb')
+ABSENT_ROOTS = ('rdkit', 'openbabel', 'lmdb', 'matplotlib')
 
 
 class _Placeholder:

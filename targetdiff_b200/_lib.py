@@ -53,6 +53,7 @@ SIGNATURES = {
     'tdiff_attn_aggregate_h': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     'tdiff_attn_aggregate_x': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     'tdiff_scatter_mean3': (_i, [_vp, _pi32, _i, _vp, _vp]),
+    'tdiff_check_stability': (_i, [_vp, _vp, _pi32, _i, _i, _vp, _vp, _vp, _vp]),
     'tdiff_launch_count': (_i64, [_vp]),
     'tdiff_edge_mlp_mode': (_i, [_vp]),
     'tdiff_profile': (_i, [_vp, _i]),

@@ -15,20 +15,26 @@
 // load-balanced over the whole GPU instead of sitting in the few warps that happen to own ligand neighbourhoods.
 __global__ void __launch_bounds__(EC_WARPS * 32)
 edge_touch_kernel(const float4* __restrict__ xm, const int* __restrict__ src, int* __restrict__ src_prev, int have_prev, int n_nodes, int k,
-                  unsigned char* __restrict__ rel_flag, unsigned char* __restrict__ touch_flag, int* __restrict__ work_list, int* __restrict__ n_work) {
+                  unsigned char* __restrict__ rel_flag, unsigned char* __restrict__ touch_flag, unsigned char* __restrict__ etype,
+                  int* __restrict__ work_list, int* __restrict__ n_work) {
   const int lane = threadIdx.x & 31;
   const int warp0 = blockIdx.x * EC_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * EC_WARPS;
   for (int node = warp0; node < n_nodes; node += nwarps) {
     const size_t e0 = (size_t)node * k;
     const float4 xd = xm[node];
     bool same = have_prev != 0, touch = xd.w != 0.0f;
+    unsigned keep_mask = 0;          // bit j/32: slot j keeps its edge type and gate (same protein neighbour as in the previous forward)
     for (int j = lane; j < k; j += 32) {
       const int s = src[e0 + j];
+      bool slot_same = false;
       if (src_prev) {
-        same = same && (src_prev[e0 + j] == s);
+        slot_same = have_prev != 0 && src_prev[e0 + j] == s;
+        same = same && slot_same;
         src_prev[e0 + j] = s;
       }
-      if (s >= 0) touch = touch || (xm[s].w != 0.0f);
+      const bool s_lig = s >= 0 && xm[s].w != 0.0f;
+      if (slot_same && !s_lig && xd.w == 0.0f) keep_mask |= 1u << (j >> 5);
+      touch = touch || s_lig;
       // "relevant" nodes = ligand atoms and their neighbours: the only rows the h2x sub-layers (and the last x2h) need
       if (rel_flag && xd.w != 0.0f && s >= 0) rel_flag[s] = 1;
     }
@@ -39,6 +45,10 @@ edge_touch_kernel(const float4* __restrict__ xm, const int* __restrict__ src, in
     // from their ligand-free values (engine.cu, ligand-free cache)
     if (touch_flag && lane == 0) touch_flag[node] = touch ? 1 : 0;
     if (same && !touch) continue;
+    // the node's edges are re-evaluated by edge_gate_kernel, except slots that still hold the same PROTEIN neighbour of a protein node:
+    // neither atom moves (reference models/uni_transformer.py:205-206), so their type and gate are unchanged -- marked with bit 7
+    for (int j = lane; j < k; j += 32)
+      if (keep_mask & (1u << (j >> 5))) etype[e0 + j] |= 0x80;
     if (lane == 0) work_list[atomicAdd(n_work, 1)] = node;
   }
 }
@@ -63,6 +73,11 @@ edge_gate_kernel(const float4* __restrict__ xm, const int* __restrict__ src, con
   for (long long item = warp0; item < n_items; item += nwarps) {
     const int node = work_list[item / k];
     const size_t e = (size_t)node * k + (size_t)(item % k);
+    const unsigned char keep = etype[e];
+    if (keep & 0x80) {               // unchanged protein-protein slot (edge_touch_kernel): keep type and gate, clear the mark
+      if (lane == 0) etype[e] = keep & 0x7f;
+      continue;
+    }
     const int s = src[e];
     if (s < 0) {
       if (lane == 0) { etype[e] = 3; e_w[e] = 0.0f; }
@@ -111,7 +126,7 @@ void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int h
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (rel_flag) cudaMemsetAsync(rel_flag, 0, (size_t)n_nodes, st);
   cudaMemsetAsync(n_work, 0, sizeof(int), st);
-  edge_touch_kernel<<<blocks, EC_WARPS * 32, 0, st>>>(xm, src, src_prev, have_prev, n_nodes, k, rel_flag, touch_flag, work_list, n_work);
+  edge_touch_kernel<<<blocks, EC_WARPS * 32, 0, st>>>(xm, src, src_prev, have_prev, n_nodes, k, rel_flag, touch_flag, etype, work_list, n_work);
   edge_gate_kernel<<<148 * 8, EC_WARPS * 32, 0, st>>>(xm, src, work_list, n_work, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2, etype, e_w, gate_mode);
 }
 

@@ -21,7 +21,7 @@
 // CTA = 28 warps, one CTA per SM, persistent over tiles of 128 edge rows:
 //   warps  0-7   epilogue      TMEM D -> +b2 -> logits / softmax weights / fused attention aggregation / plain rows   (72 regs)
 //   warps  8-11  gather        32 rows each: cp.async 512 B rows of P[src] -> S, the tile's few P[dst] rows -> D; warp 11 also
-//                              issues the MMAs                                                                        (40)
+//                              issues the MMAs                                                                        (48)
 //   warps 12-27  row threads   warp 12+q+4*qq: rows 32q..32q+31, feature quarter qq                                   (80)
 // Shared memory (208 KB): W2 pieces 64 KB | S fp32 72 KB (row stride 144 B) | G pieces 32 KB | class table pieces 32 KB | 4 KB exchange
 //                         | 4 KB destination rows.
@@ -125,6 +125,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
       "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
 // K-major SWIZZLE_128B UMMA descriptor (8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t a) {
   return (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -172,7 +175,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // LayerNorm affine parameters and the output bias travel as a kernel argument (constant bank, read with 128-bit loads)
-struct LnParams { float4 g4[32]; float4 b4[32]; float b2[128]; };
+struct LnParams { float4 g4[32]; float4 b4[32]; float b2[128]; float mu[20]; };      // + the layer's gaussian centres
 // Fused attention in the epilogues (k == 32: the 32 rows of an epilogue warp are exactly the edges of one destination), reference
 // models/uni_transformer.py:73-83:  key launch writes softmax_e(q.k/sqrt 8) * e_w, value launch does h[dst] += sum_e w * v.
 struct AggArgs {
@@ -222,8 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, const unsigned char* __restrict__ etype,
                    const float* __restrict__ dist_arr, const int* __restrict__ row_nodes, long long n_dst, long long split_dst,
                    const int* __restrict__ d_counts, int k, int offA, int offB, const unsigned char* __restrict__ w2_image,
-                   const unsigned char* __restrict__ tab_image, const float* __restrict__ offsets, float coeff,
-                   const float* __restrict__ qnode, float* __restrict__ out, int out_by_slot, AggArgs agg, const __grid_constant__ LnParams lp) {
+                   const unsigned char* __restrict__ tab_image, float coeff, const float* __restrict__ qnode, float* __restrict__ out, int out_by_slot, AggArgs agg, const __grid_constant__ LnParams lp) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sW = sbase + oW, sG = sbase + oG, sT = sbase + oT, sS = sbase + oS, sX = sbase + oX, sD = sbase + oD, sBar = sbase + oBar;
@@ -243,8 +245,8 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
   const long long n_rows = n_dst * k, split_rows = split_dst * k;      // both multiples of 128 by construction of the lists
   const long long n_tiles = (n_rows + 127) / 128;
   const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  // destination rows are staged in shared memory when a tile can only span a few destinations (k >= 19); else read from global memory
-  const bool stage_dst = 128 / k + 2 <= kDstSlots;
+  // (the tile's destination rows are staged in shared memory: a tile spans at most 128 / k + 2 <= kDstSlots destinations, k >= 19 -- checked
+  // by the launcher)
   auto tile_class = [&](long long t) -> int { return ((long long)(blockIdx.x + t * (long long)gridDim.x) * 128 >= split_rows) ? 1 : 0; };
 
   // ---- one-time setup: weight image and the first tile's class table -> smem, barriers, TMEM
@@ -287,16 +289,13 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
     reg_inc<80>();
     const int rwp = warp - kRowWarp0, q = rwp & 3, qq = rwp >> 2;
     const int r = 32 * q + lane;                    // row of the tile == TMEM lane
-    float mu[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) mu[i] = offsets[5 * qq + i];
     const float coeff2 = coeff * 1.4426950408889634f;
     const uint32_t s_row = sS + (uint32_t)qq * kSAtom + (uint32_t)r * kSRow;
     const uint32_t g_row = sG + (uint32_t)r * 128u;
     const uint32_t xslot = sX + (uint32_t)r * 4u;          // exchange slots of this row: set 0 (sums) / set 1 at +2048, quarter qq at + qq*512
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
-    // metadata of this thread's row in tile `t` (s < 0: absent edge / padding destination / beyond the end)
-    // dst_: with staged destination rows the slot of the row's destination inside the tile's D block, else the destination node
+    // metadata of this thread's row in tile `t` (s < 0: absent edge / padding destination / beyond the end); dst_ = slot of the row's
+    // destination inside the tile's staged D block
     auto load_md = [&](long long t, int& s_, int& ty_, int& dst_, float& dist_) {
       s_ = -1; ty_ = 3; dst_ = 0; dist_ = 0.f;
       if (t < my_tiles) {
@@ -306,7 +305,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
           const unsigned a = row_dst(idx, j);
           const int d = row_nodes[a];
           if (d >= 0) {
-            dst_ = stage_dst ? (int)(a - row_dst(idx0, j0)) : d;
+            dst_ = (int)(a - row_dst(idx0, j0));
             const size_t e = (size_t)d * k + j;
             s_ = src[e]; ty_ = etype[e]; dist_ = dist_arr[e];
           }
@@ -320,7 +319,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       float gv[8];
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        const float t = dist_ - mu[i];
+        const float t = dist_ - lp.mu[5 * qq + i];
         gv[i] = ok ? ex2_approx(coeff2 * (t * t)) : 0.0f;          // exp(coeff t^2); the bf16 split below keeps 16 bits of it
       }
       gv[5] = (ok && qq == 3) ? 1.0f : 0.0f;
@@ -347,52 +346,35 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
     load_md(1, s1, t1, d1, dist1);
     for (long long it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
-      const bool valid = s0 >= 0;
-      // ---- P[dst, offA + 32*qq ..] (rows of a warp usually share the destination: broadcast loads) stays in flight while we wait
-      //      for the gathered source row in the staging tile
-      float4 av[8];
-      if (!stage_dst) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) av[c] = __ldg(reinterpret_cast<const float4*>(P + (size_t)d0 * TD_NPROJ + offA + 32 * qq + 4 * c));
-        }
-      }
+      // ---- the gaussian/type block from the tensor core goes straight into the row registers ...
       f2 x[16];
-      mbar_wait(bar(B_S_FULL), ph);
-      if (stage_dst) {                  // the destination row quarter from the staged D block (rows of a warp mostly share it: broadcast reads)
-        const uint32_t d_row = sD + (uint32_t)d0 * 512u + (uint32_t)qq * 128u;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) av[c] = lds128(d_row + 16u * c);
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = lds128(s_row + 16u * c);
-        x[2 * c] = add2(pk2(v.x, v.y), pk2(av[c].x, av[c].y)); x[2 * c + 1] = add2(pk2(v.z, v.w), pk2(av[c].z, av[c].w));
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_S_EMPTY));
-      // ---- + gaussian/type block from the tensor core
       mbar_wait(bar(B_DPRE_FULL), ph);
       tc_fence_after();
       {
-        uint32_t v0[16], v1[16];
-        const uint32_t ta = t_lane + kColDpre + (uint32_t)(32 * qq);
-        tmem_ld16_nowait(ta, v0);
-        tmem_ld16_nowait(ta + 16u, v1);
-        tmem_ld_wait();
+        uint32_t v[32];
+        tmem_ld32(t_lane + kColDpre + (uint32_t)(32 * qq), v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          x[i] = add2(x[i], pk2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1])));
-          x[8 + i] = add2(x[8 + i], pk2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1])));
-        }
+        for (int i = 0; i < 16; ++i) x[i] = pk2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
       }
       tc_fence_before();
+      // ---- ... then the gathered source row (staging tile S) and the destination row quarter (staged D block; the rows of a warp
+      //      mostly share it: broadcast reads) are added chunk by chunk
+      mbar_wait(bar(B_S_FULL), ph);
+      {
+        const uint32_t d_row = sD + (uint32_t)d0 * 512u + (uint32_t)qq * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = lds128(s_row + 16u * c), w = lds128(d_row + 16u * c);
+          x[2 * c] = add2(x[2 * c], add2(pk2(v.x, v.y), pk2(w.x, w.y)));
+          x[2 * c + 1] = add2(x[2 * c + 1], add2(pk2(v.z, v.w), pk2(w.z, w.w)));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_S_EMPTY));
       // ---- gaussians of the NEXT tile now (the small MMA and its round trip overlap this tile's LayerNorm), metadata two ahead
       if (it + 1 < my_tiles) write_g(s1, t1, dist1);
       s0 = s1; t0 = t1; d0 = d1; dist0 = dist1;
       load_md(it + 2, s1, t1, d1, dist1);
-      if (!stage_dst && s0 >= 0) prefetch_l1(P + (size_t)d0 * TD_NPROJ + offA + 32 * qq);      // next tile's destination row quarter -> L1
       // ---- LayerNorm over the 128 features of the row: 4 threads (feature quarters) exchange partial sums through smem.
       //      Slot set 0 is rewritten only after every thread passed this tile's second barrier, set 1 only after the next tile's first.
       f2 sa = add2(x[0], x[1]), sb = add2(x[2], x[3]), sc = add2(x[4], x[5]), sd = add2(x[6], x[7]);
@@ -414,25 +396,29 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       named_bar_sync(1 + q, 128);
       const float var = ((lds32f(xslot + 2048u) + lds32f(xslot + 2560u)) + (lds32f(xslot + 3072u) + lds32f(xslot + 3584u))) * (1.0f / 128.0f);
       const float rstd = rsqrtf(var + 1e-5f);
-      // ---- affine + ReLU, bf16 split -> this row's 32 features of both A pieces (16 packed columns each) in tensor memory.
-      //      Absent rows carry x = 0: their (finite) outputs are never consumed.
-      uint32_t hi[16], lo[16];
-      {
-        const f2 rstd2 = pk2(rstd, rstd);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 g = lp.g4[8 * qq + c], b = lp.b4[8 * qq + c];
-          float y0, y1, y2, y3;
-          upk2(fma2(x[2 * c], mul2(rstd2, pk2(g.x, g.y)), pk2(b.x, b.y)), y0, y1);
-          upk2(fma2(x[2 * c + 1], mul2(rstd2, pk2(g.z, g.w)), pk2(b.z, b.w)), y2, y3);
-          split2(fmaxf(y0, 0.f), fmaxf(y1, 0.f), hi[2 * c], lo[2 * c]);
-          split2(fmaxf(y2, 0.f), fmaxf(y3, 0.f), hi[2 * c + 1], lo[2 * c + 1]);
-        }
-      }
+      // ---- affine + ReLU, bf16 split -> this row's 32 features of both A pieces in tensor memory, 8 features (4 packed columns) at a
+      //      time to keep few registers live.  Absent rows carry x = 0: their (finite) outputs are never consumed.
       mbar_wait(bar(B_A_EMPTY), ph ^ 1u);         // the previous tile's MMAs have read A
       tc_fence_after();
-      tmem_st16(t_lane + kColA + (uint32_t)(16 * qq), hi);
-      tmem_st16(t_lane + kColA + 64u + (uint32_t)(16 * qq), lo);
+      {
+        const f2 rstd2 = pk2(rstd, rstd);
+        const uint32_t ta = t_lane + kColA + (uint32_t)(16 * qq);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 g = lp.g4[8 * qq + 2 * c + u], b = lp.b4[8 * qq + 2 * c + u];
+            float y0, y1, y2, y3;
+            upk2(fma2(x[4 * c + 2 * u], mul2(rstd2, pk2(g.x, g.y)), pk2(b.x, b.y)), y0, y1);
+            upk2(fma2(x[4 * c + 2 * u + 1], mul2(rstd2, pk2(g.z, g.w)), pk2(b.z, b.w)), y2, y3);
+            split2(fmaxf(y0, 0.f), fmaxf(y1, 0.f), hi[2 * u], lo[2 * u]);
+            split2(fmaxf(y2, 0.f), fmaxf(y3, 0.f), hi[2 * u + 1], lo[2 * u + 1]);
+          }
+          tmem_st4(ta + 4u * c, hi);
+          tmem_st4(ta + 64u + 4u * c, lo);
+        }
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -441,7 +427,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
   } else if (warp >= kGatherWarp0) {
     // ================================================================= gather warps (lane = 4 features), 32 rows each; the last one
     //                                                                   also issues the MMAs (one thread) between its copies
-    reg_dec<40>();     // register budget: 256*72 (epilogue, launch value) + 128*40 (gather / MMA) + 512*80 (rows) = 64512 = 896 x 72
+    reg_dec<48>();     // register budget: 256*72 (epilogue, launch value) + 128*48 (gather / MMA) + 512*80 (rows) = 65536
     const int gw = warp - kGatherWarp0;
     const bool mma_warp = warp == kMmaWarp;
     const int atom = lane >> 3, ch = lane & 7;
@@ -530,7 +516,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
           if (sr >= 0) cp_async16(dsta, P + (size_t)sr * TD_NPROJ + offB + 4 * lane);
           else sts128f(dsta, make_float4(0.f, 0.f, 0.f, 0.f));
         }
-        if (stage_dst) {
+        {
           // ---- the tile's destination rows P[dst, offA + 4*lane ..] -> D (512 B each); absent rows read zeros through S, so padding
           //      destinations only need defined bytes
           const long long idx0 = (blockIdx.x + it * (long long)gridDim.x) * 128;
@@ -729,7 +715,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
 
 // n_dst destinations (device counts {n_dst, split_dst} in d_counts override the host values); see the kernel comment for the row model
 void td_launch_edge_mlp_v4(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_dst,
-                           long long split_dst, const int* d_counts, int k, const TdMlp& m, const float* offsets, float coeff,
+                           long long split_dst, const int* d_counts, int k, const TdMlp& m, const float* h_offsets, float coeff,
                            const float* h_ln_g, const float* h_ln_b, const float* h_b2, const float* qnode, float* out, int out_by_slot,
                            const float* agg_logits, const float* agg_e_w, float* agg_h, int key_softmax, int sm_count, cudaStream_t st) {
   if (n_dst == 0) return;
@@ -738,6 +724,7 @@ void td_launch_edge_mlp_v4(const float* P, const int* src, const unsigned char* 
   memcpy(lp.b4, h_ln_b, sizeof(lp.b4));
   memset(lp.b2, 0, sizeof(lp.b2));
   memcpy(lp.b2, h_b2, sizeof(float) * (size_t)m.nout);
+  memcpy(lp.mu, h_offsets, sizeof(lp.mu));
   static size_t opted128[TD_MAX_DEVICES] = {0}, opted16[TD_MAX_DEVICES] = {0};
   td_opt_in_smem(edge_mlp_v4_kernel<128>, kSmem, opted128);
   td_opt_in_smem(edge_mlp_v4_kernel<16>, kSmem, opted16);
@@ -746,8 +733,8 @@ void td_launch_edge_mlp_v4(const float* P, const int* src, const unsigned char* 
   AggArgs agg = {agg_logits, agg_e_w, agg_h, (key_softmax && k == 32) ? 1 : 0};
   if (m.nout == 16)
     edge_mlp_v4_kernel<16><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_dst, split_dst, d_counts, k, m.offA, m.offB, m.w2_img,
-                                                         m.tabcls_img, offsets, coeff, nullptr, out, out_by_slot, agg, lp);
+                                                         m.tabcls_img, coeff, nullptr, out, out_by_slot, agg, lp);
   else
     edge_mlp_v4_kernel<128><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_dst, split_dst, d_counts, k, m.offA, m.offB, m.w2_img,
-                                                          m.tabcls_img, offsets, coeff, qnode, out, out_by_slot, agg, lp);
+                                                          m.tabcls_img, coeff, qnode, out, out_by_slot, agg, lp);
 }

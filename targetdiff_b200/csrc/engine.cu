@@ -460,6 +460,7 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     else if (!strcmp(mode, "tc6")) e->mlp_mode = 3;
     else { cudaFree(e->arena); cudaFree(e->img_arena); delete e; return set_err(TDIFF_EINVAL, "TDIFF_EDGE_MLP=%s (simt|tc3|tc3v2|tc6)", mode); }
   }
+  if (cfg->knn < 19) e->mlp_v4 = false;          // the v4 edge kernel stages <= 8 destination rows per 128-row tile; tiny k runs the previous kernel
   if ((cfg->ew_net_type != 0 || cfg->x2h_out_fc) && !(e->mlp_mode == 2 && e->mlp_v4)) {
     cudaFree(e->arena); cudaFree(e->img_arena); delete e;
     return set_err(TDIFF_EINVAL, "ew_net_type != 'global' and x2h_out_fc are implemented by the default engine mode only (unset TDIFF_EDGE_MLP)");
@@ -713,7 +714,7 @@ void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src,
     // plain (unfused) x2h outputs are consumed by slot index (aggregate_h_logits_kernel); everything else by row index
     const int by_slot = (list != ROWS_LIGAND && !key_softmax && agg_logits == nullptr) ? 1 : 0;
     td_launch_edge_mlp_v4(P, src, etype, e->dist.as<float>(), rows, n_dst, split, counts, K, m,
-                          offsets, coeff, e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena),
+                          e->host_arena.data() + (offsets - e->arena), coeff, e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena),
                           e->host_arena.data() + (m.b2 - e->arena), qnode, out, by_slot, agg_logits, e_w, agg_h, key_softmax,
                           e->sm_count, st);
     return;
@@ -1184,6 +1185,31 @@ extern "C" int tdiff_scatter_mean3(const float* d_src, const int32_t* h_counts, 
   if (ce == cudaSuccess) ce = cudaGetLastError();
   dptr.release(); o4.release();
   if (ce != cudaSuccess) return set_err(TDIFF_ECUDA, "scatter_mean3: %s", cudaGetErrorString(ce));
+  return TDIFF_OK;
+}
+
+extern "C" int tdiff_check_stability(const float* d_pos, const int32_t* d_atomic_num, const int32_t* h_counts, int n_mol, int hs, int32_t* d_nr_bonds,
+                                     int32_t* d_stable_atoms, uint8_t* d_mol_stable, void* stream) {
+  if (!d_pos || !d_atomic_num || !h_counts || !d_stable_atoms || !d_mol_stable || n_mol < 0) return set_err(TDIFF_EINVAL, "check_stability: bad arguments");
+  if (n_mol == 0) return TDIFF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int> ptr(n_mol + 1, 0);
+  for (int m = 0; m < n_mol; ++m) {
+    if (h_counts[m] < 0) return set_err(TDIFF_EINVAL, "negative atom count");
+    ptr[m + 1] = ptr[m] + h_counts[m];
+  }
+  DevBuf dptr, derr;
+  if (dptr.ensure((n_mol + 1) * 4) || derr.ensure(4)) { dptr.release(); derr.release(); return set_err(TDIFF_ECUDA, "out of device memory"); }
+  cudaMemcpyAsync(dptr.p, ptr.data(), (n_mol + 1) * 4, cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(derr.p, 0, 4, st);
+  td_launch_check_stability(d_pos, d_atomic_num, dptr.as<int>(), n_mol, hs, d_nr_bonds, d_stable_atoms, d_mol_stable, derr.as<int>(), st);
+  int flag = 0;
+  cudaMemcpyAsync(&flag, derr.p, 4, cudaMemcpyDeviceToHost, st);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  dptr.release(); derr.release();
+  if (ce != cudaSuccess) return set_err(TDIFF_ECUDA, "check_stability: %s", cudaGetErrorString(ce));
+  if (flag) return set_err(TDIFF_EINVAL, "check_stability: atomic number outside the reference's table (H C N O F P S Cl)");
   return TDIFF_OK;
 }
 

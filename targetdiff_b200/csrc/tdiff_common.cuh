@@ -169,7 +169,7 @@ void td_launch_edge_mlp_tc(const float* P, const float4* xm, const int* src, con
                            const int* row_nodes, long long n_rows, int k, TdMlp m, const unsigned char* w2_image, int pieces, const float* offsets, float coeff,
                            float* out, int sm_count, cudaStream_t st);
 void td_launch_edge_mlp_v4(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_dst,
-                           long long split_dst, const int* d_counts, int k, const TdMlp& m, const float* offsets, float coeff,
+                           long long split_dst, const int* d_counts, int k, const TdMlp& m, const float* h_offsets, float coeff,
                            const float* h_ln_g, const float* h_ln_b, const float* h_b2, const float* qnode, float* out, int out_by_slot,
                            const float* agg_logits, const float* agg_e_w, float* agg_h, int key_softmax, int sm_count, cudaStream_t st);
 void td_launch_rows_tc(int mode, const float* in, int ldi, int in_off, long long n_rows, TdMlp m, const unsigned char* w_image, int pieces, float* out,
@@ -185,3 +185,5 @@ void td_launch_aggregate_x_logits(const float* logits, const float* v16, const f
                                   const int* row_nodes, float4* xm_out, int n_rows, int k, cudaStream_t st);
 void td_launch_head(const float* h, const int* lig_node, int n_lig, const float* w1t, const float* b1, const float* w2, const float* b2,
                     int n_classes, float* logits, cudaStream_t st);
+void td_launch_check_stability(const float* pos, const int* atomic_num, const int* mol_ptr, int n_mol, int hs, int* nr_bonds, int* stable_atoms,
+                               unsigned char* mol_stable, int* err, cudaStream_t st);

@@ -253,3 +253,30 @@ def test_errors_are_loud():
     with pytest.raises(ValueError):
         model(b['protein_pos'], b['protein_v'], b['batch_protein'].flip(0) * 0 + torch.arange(40, device=_dev()).flip(0) // 20,
               b['init_ligand_pos'], b['init_ligand_v'], b['batch_ligand'])
+
+
+def test_check_stability_vs_oracle():
+    """tdiff_check_stability against the CPU restatement of utils/evaluation/analyze.py:106-143 -- integer outputs,
+    bit-exact; ragged molecule sizes incl. a single atom, both `hs` settings, and the per-atom bond counts."""
+    import numpy as np
+    from targetdiff_b200 import analyze
+    rng = np.random.RandomState(1)
+    sizes = [1, 2, 9, 25, 40, 33, 86, 17]
+    pos, zs = [], []
+    for n in sizes:
+        pos.append(np.cumsum(rng.normal(scale=0.85, size=(n, 3)), axis=0).astype(np.float32).astype(np.float64) + rng.uniform(-30, 30, size=(1, 3)))
+        zs.append(rng.choice([1, 6, 7, 8, 9, 15, 16, 17], size=n, p=[0.1, 0.5, 0.12, 0.15, 0.03, 0.02, 0.05, 0.03]))
+    pos = [p.astype(np.float32).astype(np.float64) for p in pos]           # the sampler's positions are fp32 values widened to fp64
+    for hs in (False, True):
+        ms, ns, na, nb = analyze.check_stability_batch(pos, zs, hs=hs)
+        off = 0
+        for i, n in enumerate(sizes):
+            w = restate.check_stability(pos[i], zs[i], hs=hs)
+            assert (bool(ms[i]), int(ns[i]), int(na[i])) == (bool(w[0]), w[1], w[2])
+            assert np.array_equal(nb[off:off + n], w[3])
+            off += n
+    one = analyze.check_stability(pos[3], zs[3], return_nr_bonds=True)
+    w = restate.check_stability(pos[3], zs[3])
+    assert one[:3] == (bool(w[0]), w[1], w[2]) and np.array_equal(one[3], w[3])
+    with pytest.raises(Exception):
+        analyze.check_stability(pos[1], np.array([6, 5]))                  # boron is not in the reference's table (KeyError there)

@@ -182,3 +182,20 @@ def test_sampling_driver_restatement_bit_exact():
     from targetdiff_b200.pocket import pdb_to_pocket_data
     mine = pdb_to_pocket_data(os.path.join(root, 'tests', 'golden', '1h36_pocket10.pdb'))
     assert torch.equal(mine.protein_pos, data.protein_pos) and torch.equal(mine.protein_atom_feature, data.protein_atom_feature)
+
+
+def test_check_stability_restatement_equals_reference():
+    """n4: the bond-count stability screen (utils/evaluation/analyze.py:106-143) on random molecule-like point sets."""
+    import numpy as np
+    refload.import_reference_scripts()          # installs the placeholders (matplotlib) the module imports at the top
+    import importlib
+    analyze = importlib.import_module('utils.evaluation.analyze')
+    rng = np.random.RandomState(0)
+    for n in (1, 2, 9, 25, 40):
+        for hs in (False, True):
+            pos = np.cumsum(rng.normal(scale=0.85, size=(n, 3)), axis=0)          # chain-like: neighbours at bonding distance
+            z = rng.choice([1, 6, 7, 8, 9, 15, 16, 17], size=n, p=[0.1, 0.5, 0.12, 0.15, 0.03, 0.02, 0.05, 0.03])
+            want = analyze.check_stability(pos, z, hs=hs, return_nr_bonds=True)
+            got = restate.check_stability(pos, z, hs=hs)
+            assert (bool(want[0]), want[1], want[2]) == (bool(got[0]), got[1], got[2])
+            assert np.array_equal(want[3], got[3])

@@ -21,7 +21,7 @@
 // CTA = 28 warps, one CTA per SM, persistent over tiles of 128 edge rows:
 //   warps  0-7   epilogue      TMEM D -> +b2 -> logits / softmax weights / fused attention aggregation / plain rows   (72 regs)
 //   warps  8-11  gather        32 rows each: cp.async 512 B rows of P[src] -> S, the tile's few P[dst] rows -> D; warp 11 also
-//                              issues the MMAs                                                                        (48)
+//                              issues the MMAs                                                                        (40)
 //   warps 12-27  row threads   warp 12+q+4*qq: rows 32q..32q+31, feature quarter qq                                   (80)
 // Shared memory (208 KB): W2 pieces 64 KB | S fp32 72 KB (row stride 144 B) | G pieces 32 KB | class table pieces 32 KB | 4 KB exchange
 //                         | 4 KB destination rows.
@@ -421,7 +421,10 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
   } else if (warp >= kGatherWarp0) {
     // ================================================================= gather warps (lane = 4 features), 32 rows each; the last one
     //                                                                   also issues the MMAs (one thread) between its copies
-    reg_dec<48>();     // register budget: 256*72 (epilogue, launch value) + 128*48 (gather / MMA) + 512*80 (rows) = 65536
+    // Register budget.  The CTA is launched with 72 registers x 896 threads; setmaxnreg only moves registers INSIDE that allocation:
+    // the gather warps must release (72 - 40) x 128 = 4096 so that the row warps' increase of (80 - 72) x 512 = 4096 can be granted
+    // (a smaller release leaves the row warps blocked in setmaxnreg.inc forever).
+    reg_dec<40>();
     const int gw = warp - kGatherWarp0;
     const bool mma_warp = warp == kMmaWarp;
     const int atom = lane >> 3, ch = lane & 7;

@@ -4,6 +4,11 @@
 tag=${1:-r02}; shift
 what=${*:-tests bench ncu}
 mkdir -p gpurun_out
+# gate: a tiny forward + chain against the oracle under a short timeout -- a hung or wrong kernel stops the whole call here
+if ! timeout 240 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; then
+  echo "SMOKE FAILED / TIMED OUT -- aborting"; tail -5 gpurun_out/${tag}_smoke.log; exit 1
+fi
+tail -1 gpurun_out/${tag}_smoke.log
 for w in $what; do
   case $w in
     tests) timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; tail -3 gpurun_out/${tag}_pytest_gpu.log ;;

@@ -47,8 +47,9 @@ edge_touch_kernel(const float4* __restrict__ xm, const int* __restrict__ src, in
     if (same && !touch) continue;
     // the node's edges are re-evaluated by edge_gate_kernel, except slots that still hold the same PROTEIN neighbour of a protein node:
     // neither atom moves (reference models/uni_transformer.py:205-206), so their type and gate are unchanged -- marked with bit 7
-    for (int j = lane; j < k; j += 32)
-      if (keep_mask & (1u << (j >> 5))) etype[e0 + j] |= 0x80;
+    if (etype)
+      for (int j = lane; j < k; j += 32)
+        if (keep_mask & (1u << (j >> 5))) etype[e0 + j] |= 0x80;
     if (lane == 0) work_list[atomicAdd(n_work, 1)] = node;
   }
 }
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(EC_WARPS * 32)
 edge_gate_kernel(const float4* __restrict__ xm, const int* __restrict__ src, const int* __restrict__ work_list, const int* __restrict__ n_work,
                  int k, const float* __restrict__ offsets, float coeff, const float* __restrict__ w1t, const float* __restrict__ b1,
                  const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ w2, float b2,
-                 unsigned char* __restrict__ etype, float* __restrict__ e_w, int gate_mode) {
+                 unsigned char* __restrict__ etype, float* __restrict__ e_w, int gate_mode, int honour_keep) {
   __shared__ float s_w1t[TD_NG * TD_H];
   __shared__ float s_b1[TD_H], s_g[TD_H], s_b[TD_H], s_w2[TD_H];
   for (int i = threadIdx.x; i < TD_NG * TD_H; i += blockDim.x) s_w1t[i] = w1t[i];
@@ -73,7 +74,7 @@ edge_gate_kernel(const float4* __restrict__ xm, const int* __restrict__ src, con
   for (long long item = warp0; item < n_items; item += nwarps) {
     const int node = work_list[item / k];
     const size_t e = (size_t)node * k + (size_t)(item % k);
-    const unsigned char keep = etype[e];
+    const unsigned char keep = honour_keep ? etype[e] : 0;      // first forward of a batch: `etype` holds no marks yet (and no valid types)
     if (keep & 0x80) {               // unchanged protein-protein slot (edge_touch_kernel): keep type and gate, clear the mark
       if (lane == 0) etype[e] = keep & 0x7f;
       continue;
@@ -126,8 +127,11 @@ void td_launch_edge_const(const float4* xm, const int* src, int* src_prev, int h
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (rel_flag) cudaMemsetAsync(rel_flag, 0, (size_t)n_nodes, st);
   cudaMemsetAsync(n_work, 0, sizeof(int), st);
-  edge_touch_kernel<<<blocks, EC_WARPS * 32, 0, st>>>(xm, src, src_prev, have_prev, n_nodes, k, rel_flag, touch_flag, etype, work_list, n_work);
-  edge_gate_kernel<<<148 * 8, EC_WARPS * 32, 0, st>>>(xm, src, work_list, n_work, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2, etype, e_w, gate_mode);
+  // gate_mode bit 0: no global gate (ew_net_type r / m / none); bit 1: developer switch, re-evaluate every slot of a listed node
+  edge_touch_kernel<<<blocks, EC_WARPS * 32, 0, st>>>(xm, src, src_prev, have_prev, n_nodes, k, rel_flag, touch_flag, (gate_mode & 2) ? nullptr : etype,
+                                                      work_list, n_work);
+  edge_gate_kernel<<<148 * 8, EC_WARPS * 32, 0, st>>>(xm, src, work_list, n_work, k, offsets, coeff, w1t, b1, ln_g, ln_b, w2, b2, etype, e_w, gate_mode & 1,
+                                                     (have_prev && !(gate_mode & 2)) ? 1 : 0);
 }
 
 // Per-layer edge length |x_dst - x_src| (reference models/uni_transformer.py:188-189) for every slot, from the layer's input

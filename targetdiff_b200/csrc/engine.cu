@@ -47,6 +47,10 @@ struct DevBuf {
     size_t want = bytes + bytes / 8 + 256;
     if (cudaMalloc(&p, want) != cudaSuccess) { (void)cudaGetLastError(); if (cudaMalloc(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); return -1; } want = bytes; }
     cap = want;
+    // test switch: fill fresh allocations with 0xFF (NaN floats, negative ints) so that a read of never-written memory shows up in
+    // the parity tests instead of depending on what the allocator returns (the GPU test-suite runs with it, tests/conftest.py)
+    static const bool poison = getenv("TDIFF_POISON") != nullptr;
+    if (poison) cudaMemset(p, 0xFF, want);
     return 0;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -83,7 +87,7 @@ struct tdiff_engine {
   bool knn_incremental = false;         // protein-protein neighbour keys cached at bind time (TDIFF_KNN_FULL=1 disables)
   bool have_prev = false;               // src_prev / etype / e_w hold the previous forward's graph of this batch (edge_const reuse)
   // developer switches, read from the environment ONCE in tdiff_create (never on the per-layer path)
-  bool env_no_fused_agg = false, env_no_restrict = false, env_no_graph = false, env_knn_full = false;
+  bool env_no_fused_agg = false, env_no_restrict = false, env_no_graph = false, env_knn_full = false, env_no_slot_keep = false;
   int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
   DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
   DevBuf rel_flag, rel_list, n_rel, work_list, n_work, knn_cache;
@@ -469,6 +473,7 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
   e->env_no_restrict = getenv("TDIFF_NO_RESTRICT") != nullptr;
   e->env_no_graph = getenv("TDIFF_NO_GRAPH") != nullptr;
   e->env_knn_full = getenv("TDIFF_KNN_FULL") != nullptr;
+  e->env_no_slot_keep = getenv("TDIFF_NO_SLOT_KEEP") != nullptr;
   if (const char* fd = getenv("TDIFF_FREE_DEPTH")) e->env_free_depth = atoi(fd) < 0 ? 0 : (atoi(fd) > 8 ? 8 : atoi(fd));
   e->host_arena = pk.host;
   const float* A = e->arena;
@@ -626,6 +631,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   CK(cudaMemsetAsync(e->h0.p, 0, (size_t)N * TD_H * 4, st));
   CK(cudaMemsetAsync(e->xm0.p, 0, (size_t)N * 16, st));
   CK(cudaMemsetAsync(e->xm1.p, 0, (size_t)N * 16, st));
+  CK(cudaMemsetAsync(e->etype.p, 0, slots, st));            // bit 7 of an edge type is the "keep" mark of the incremental edge gate
   if (center_mode == 1) td_launch_segment_mean3(d_ppos, e->prot_ptr.as<int>(), B, e->offset.as<float4>(), st);
   td_launch_place_protein(d_ppos, e->prot_node.as<int>(), e->prot_graph.as<int>(), e->offset.as<float4>(), (int)Np, e->xm0.as<float4>(),
                           e->xm1.as<float4>(), st);
@@ -768,7 +774,7 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x, int free_build = 0
       td_launch_knn(xm[cur], e->node_ptr.as<int>(), e->B, e->max_ng, K, e->src.as<int>(), st);
     td_launch_edge_const(xm[cur], src, e->src_prev.as<int>(), e->have_prev ? 1 : 0, N, K, e->ew_off, e->ew_coeff, e->ew_w1t, e->ew_b1, e->ew_g, e->ew_b, e->ew_w2,
                          e->ew_b2, e->etype.as<unsigned char>(), e->e_w.as<float>(), e->rel_flag.as<unsigned char>(),
-                         use_free ? e->dirty.as<unsigned char>() : nullptr, e->work_list.as<int>(), e->n_work.as<int>(), e->ew_mode != 0 ? 1 : 0, st);
+                         use_free ? e->dirty.as<unsigned char>() : nullptr, e->work_list.as<int>(), e->n_work.as<int>(), (e->ew_mode != 0 ? 1 : 0) | (e->env_no_slot_keep ? 2 : 0), st);
     e->have_prev = true;
     for (int l = 0; l < use_free; ++l) {             // dirty sets layer by layer and their class-sorted destination lists
       unsigned char* dl = e->dirty.as<unsigned char>() + (size_t)l * N;

@@ -8,6 +8,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# every engine buffer starts as 0xFF bytes in the test-suite: reads of never-written device memory become NaNs / wild indices
+os.environ.setdefault('TDIFF_POISON', '1')
+
+
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
 

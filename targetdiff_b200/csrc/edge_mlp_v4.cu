@@ -24,7 +24,7 @@
 //                              issues the MMAs                                                                        (40)
 //   warps 12-27  row threads   warp 12+q+4*qq: rows 32q..32q+31, feature quarter qq                                   (80)
 // Shared memory (208 KB): W2 pieces 64 KB | S fp32 72 KB (row stride 144 B) | G pieces 32 KB | class table pieces 32 KB | 4 KB exchange
-//                         | 4 KB destination rows.
+//                         | 4 KB destination rows | 1 KB LayerNorm affine.
 // TMEM 512 columns: D[2] at 0/128, Dpre at 256, A pieces at 384 / 448.  bf16 split: 2 pieces / 3 products (a1b1 + a1b2 + a2b1).
 #include <stdio.h>
 #include <stdlib.h>
@@ -43,7 +43,7 @@ constexpr int kTabClassBytes = 2 * kAtom;  // one class table: 2 bf16 pieces of 
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int kDstSlots = 8;               // destination rows P[dst, offA:+128] staged per tile (a tile spans <= 128/k + 2 destinations)
 constexpr int oW = 0, oG = oW + 4 * kAtom, oT = oG + 2 * kAtom, oS = oT + 2 * kAtom, oX = oS + 4 * kSAtom, oD = oX + 2 * 2048,
-              oBar = oD + kDstSlots * 512, kSmem = oBar + 16 * 8 + 16;
+              oLN = oD + kDstSlots * 512, oBar = oLN + 1024, kSmem = oBar + 16 * 8 + 16;      // oLN: LayerNorm gain | bias, 512 B each
 enum { B_S_FULL = 0, B_S_EMPTY, B_G_FULL, B_A_FULL, B_A_EMPTY, B_DPRE_FULL, B_D_FULL0, B_D_FULL1, B_D_EMPTY0, B_D_EMPTY1 };
 constexpr uint32_t kColD = 0, kColDpre = 256, kColA = 384;
 
@@ -222,7 +222,8 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
                    const unsigned char* __restrict__ tab_image, float coeff, const float* __restrict__ qnode, float* __restrict__ out, int out_by_slot, AggArgs agg, const __grid_constant__ LnParams lp) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
-  const uint32_t sW = sbase + oW, sG = sbase + oG, sT = sbase + oT, sS = sbase + oS, sX = sbase + oX, sD = sbase + oD, sBar = sbase + oBar;
+  const uint32_t sW = sbase + oW, sG = sbase + oG, sT = sbase + oT, sS = sbase + oS, sX = sbase + oX, sD = sbase + oD, sLN = sbase + oLN,
+                 sBar = sbase + oBar;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem_raw + oBar + 16 * 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
@@ -258,6 +259,10 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       sts128(sT + 16 * i, v.x, v.y, v.z, v.w);
     }
   }
+  // LayerNorm affine parameters: kernel argument -> shared memory (the row threads read them as broadcast 128-bit loads; indexed
+  // constant-bank loads were the hottest stall of the row loop)
+  if (tid < 32) sts128f(sLN + 16u * tid, lp.g4[tid]);
+  else if (tid < 64) sts128f(sLN + 512u + 16u * (tid - 32), lp.b4[tid - 32]);
   if (tid == 0) {
     mbar_init(bar(B_S_FULL), kGatherWarps);
     mbar_init(bar(B_S_EMPTY), kRowWarps);
@@ -402,7 +407,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const float4 g = lp.g4[8 * qq + 2 * c + u], b = lp.b4[8 * qq + 2 * c + u];
+            const float4 g = lds128(sLN + 16u * (uint32_t)(8 * qq + 2 * c + u)), b = lds128(sLN + 512u + 16u * (uint32_t)(8 * qq + 2 * c + u));
             float y0, y1, y2, y3;
             upk2(fma2(x[4 * c + 2 * u], mul2(rstd2, pk2(g.x, g.y)), pk2(b.x, b.y)), y0, y1);
             upk2(fma2(x[4 * c + 2 * u + 1], mul2(rstd2, pk2(g.z, g.w)), pk2(b.z, b.w)), y2, y3);

@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtdiff.so')
+LIB_PATH = os.environ.get('TDIFF_LIB') or os.path.join(_HERE, 'libtdiff.so')      # TDIFF_LIB: developer switch (A/B of kernel builds)
 
 TDIFF_OK, TDIFF_EINVAL, TDIFF_ECUDA, TDIFF_ESTATE, TDIFF_EWEIGHT = 0, -1, -2, -3, -4
 

@@ -20,11 +20,9 @@
 //
 // CTA = 28 warps, one CTA per SM, persistent over tiles of 128 edge rows:
 //   warps  0-7   epilogue      TMEM D -> +b2 -> logits / softmax weights / fused attention aggregation / plain rows   (72 regs)
-//   warps  8-11  gather        32 rows each: cp.async 512 B rows of P[src] -> S, the tile's few P[dst] rows -> D; warp 11 also
-//                              issues the MMAs                                                                        (40)
+//   warps  8-11  gather        32 rows each: cp.async 512 B rows of P[src] -> S; warp 11 also issues the MMAs          (40)
 //   warps 12-27  row threads   warp 12+q+4*qq: rows 32q..32q+31, feature quarter qq                                   (80)
-// Shared memory (208 KB): W2 pieces 64 KB | S fp32 72 KB (row stride 144 B) | G pieces 32 KB | class table pieces 32 KB | 4 KB exchange
-//                         | 4 KB destination rows | 1 KB LayerNorm affine.
+// Shared memory (197 KB): W2 pieces 64 KB | S fp32 72 KB (row stride 144 B) | G pieces 32 KB | class table pieces 32 KB | 4 KB exchange.
 // TMEM 512 columns: D[2] at 0/128, Dpre at 256, A pieces at 384 / 448.  bf16 split: 2 pieces / 3 products (a1b1 + a1b2 + a2b1).
 #include <stdio.h>
 #include <stdlib.h>
@@ -41,9 +39,8 @@ constexpr int kSRow = 144;                 // staging row stride (128 B of data 
 constexpr int kSAtom = 128 * kSRow;        // one feature quarter of the staging tile
 constexpr int kTabClassBytes = 2 * kAtom;  // one class table: 2 bf16 pieces of [128 x 64]
 // shared-memory map (bytes from the 1024-aligned base)
-constexpr int kDstSlots = 8;               // destination rows P[dst, offA:+128] staged per tile (a tile spans <= 128/k + 2 destinations)
-constexpr int oW = 0, oG = oW + 4 * kAtom, oT = oG + 2 * kAtom, oS = oT + 2 * kAtom, oX = oS + 4 * kSAtom, oD = oX + 2 * 2048,
-              oLN = oD + kDstSlots * 512, oBar = oLN + 1024, kSmem = oBar + 16 * 8 + 16;      // oLN: LayerNorm gain | bias, 512 B each
+constexpr int oW = 0, oG = oW + 4 * kAtom, oT = oG + 2 * kAtom, oS = oT + 2 * kAtom, oX = oS + 4 * kSAtom, oBar = oX + 2 * 2048,
+              kSmem = oBar + 16 * 8 + 16;
 enum { B_S_FULL = 0, B_S_EMPTY, B_G_FULL, B_A_FULL, B_A_EMPTY, B_DPRE_FULL, B_D_FULL0, B_D_FULL1, B_D_EMPTY0, B_D_EMPTY1 };
 constexpr uint32_t kColD = 0, kColDpre = 256, kColA = 384;
 
@@ -52,14 +49,20 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-// Both waits block in hardware: try_wait with a long suspend-time hint parks the warp until the phase completes (or the hint
-// expires), so waiting warps do not burn issue slots of the SM sub-partition they share with the row threads.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+      "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(100);
+  }
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -119,9 +122,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
       "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
-}
 // K-major SWIZZLE_128B UMMA descriptor (8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t a) {
   return (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
@@ -169,7 +169,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // LayerNorm affine parameters and the output bias travel as a kernel argument (constant bank, read with 128-bit loads)
-struct LnParams { float4 g4[32]; float4 b4[32]; float b2[128]; float mu[20]; };      // + the layer's gaussian centres
+struct LnParams { float4 g4[32]; float4 b4[32]; float b2[128]; float mu[20]; };
 // Fused attention in the epilogues (k == 32: the 32 rows of an epilogue warp are exactly the edges of one destination), reference
 // models/uni_transformer.py:73-83:  key launch writes softmax_e(q.k/sqrt 8) * e_w, value launch does h[dst] += sum_e w * v.
 struct AggArgs {
@@ -222,8 +222,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
                    const unsigned char* __restrict__ tab_image, float coeff, const float* __restrict__ qnode, float* __restrict__ out, int out_by_slot, AggArgs agg, const __grid_constant__ LnParams lp) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sbase = smem_u32(smem_raw);
-  const uint32_t sW = sbase + oW, sG = sbase + oG, sT = sbase + oT, sS = sbase + oS, sX = sbase + oX, sD = sbase + oD, sLN = sbase + oLN,
-                 sBar = sbase + oBar;
+  const uint32_t sW = sbase + oW, sG = sbase + oG, sT = sbase + oT, sS = sbase + oS, sX = sbase + oX, sBar = sbase + oBar;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem_raw + oBar + 16 * 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
@@ -240,8 +239,6 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
   const long long n_rows = n_dst * k, split_rows = split_dst * k;      // both multiples of 128 by construction of the lists
   const long long n_tiles = (n_rows + 127) / 128;
   const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  // (the tile's destination rows are staged in shared memory: a tile spans at most 128 / k + 2 <= kDstSlots destinations, k >= 19 -- checked
-  // by the launcher)
   auto tile_class = [&](long long t) -> int { return ((long long)(blockIdx.x + t * (long long)gridDim.x) * 128 >= split_rows) ? 1 : 0; };
 
   // ---- one-time setup: weight image and the first tile's class table -> smem, barriers, TMEM
@@ -259,10 +256,6 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       sts128(sT + 16 * i, v.x, v.y, v.z, v.w);
     }
   }
-  // LayerNorm affine parameters: kernel argument -> shared memory (the row threads read them as broadcast 128-bit loads; indexed
-  // constant-bank loads were the hottest stall of the row loop)
-  if (tid < 32) sts128f(sLN + 16u * tid, lp.g4[tid]);
-  else if (tid < 64) sts128f(sLN + 512u + 16u * (tid - 32), lp.b4[tid - 32]);
   if (tid == 0) {
     mbar_init(bar(B_S_FULL), kGatherWarps);
     mbar_init(bar(B_S_EMPTY), kRowWarps);
@@ -288,23 +281,25 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
     reg_inc<80>();
     const int rwp = warp - kRowWarp0, q = rwp & 3, qq = rwp >> 2;
     const int r = 32 * q + lane;                    // row of the tile == TMEM lane
+    float mu[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) mu[i] = lp.mu[5 * qq + i];
     const float coeff2 = coeff * 1.4426950408889634f;
     const uint32_t s_row = sS + (uint32_t)qq * kSAtom + (uint32_t)r * kSRow;
     const uint32_t g_row = sG + (uint32_t)r * 128u;
     const uint32_t xslot = sX + (uint32_t)r * 4u;          // exchange slots of this row: set 0 (sums) / set 1 at +2048, quarter qq at + qq*512
     const uint32_t t_lane = tmem_base + ((uint32_t)(32 * q) << 16);
-    // metadata of this thread's row in tile `t` (s < 0: absent edge / padding destination / beyond the end); dst_ = slot of the row's
-    // destination inside the tile's staged D block
+    // metadata of this thread's row in tile `t` (s < 0: absent edge / padding destination / beyond the end)
     auto load_md = [&](long long t, int& s_, int& ty_, int& dst_, float& dist_) {
       s_ = -1; ty_ = 3; dst_ = 0; dist_ = 0.f;
       if (t < my_tiles) {
-        const long long idx0 = (blockIdx.x + t * (long long)gridDim.x) * 128, idx = idx0 + r;
+        const long long idx = (blockIdx.x + t * (long long)gridDim.x) * 128 + r;
         if (idx < n_rows) {
-          int j, j0;
+          int j;
           const unsigned a = row_dst(idx, j);
           const int d = row_nodes[a];
           if (d >= 0) {
-            dst_ = (int)(a - row_dst(idx0, j0));
+            dst_ = d;
             const size_t e = (size_t)d * k + j;
             s_ = src[e]; ty_ = etype[e]; dist_ = dist_arr[e];
           }
@@ -318,7 +313,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       float gv[8];
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        const float t = dist_ - lp.mu[5 * qq + i];
+        const float t = dist_ - mu[i];
         gv[i] = ok ? ex2_approx(coeff2 * (t * t)) : 0.0f;          // exp(coeff t^2); the bf16 split below keeps 16 bits of it
       }
       gv[5] = (ok && qq == 3) ? 1.0f : 0.0f;
@@ -345,35 +340,45 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
     load_md(1, s1, t1, d1, dist1);
     for (long long it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
-      // ---- the gaussian/type block from the tensor core goes straight into the row registers ...
-      f2 x[16];
-      mbar_wait(bar(B_DPRE_FULL), ph);
-      tc_fence_after();
-      {
-        uint32_t v[32];
-        tmem_ld32(t_lane + kColDpre + (uint32_t)(32 * qq), v);
+      const bool valid = s0 >= 0;
+      // ---- P[dst, offA + 32*qq ..] (rows of a warp usually share the destination: broadcast loads) stays in flight while we wait
+      //      for the gathered source row in the staging tile
+      float4 av[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = pk2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      for (int c = 0; c < 8; ++c) {
+        av[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) av[c] = __ldg(reinterpret_cast<const float4*>(P + (size_t)d0 * TD_NPROJ + offA + 32 * qq + 4 * c));
       }
-      tc_fence_before();
-      // ---- ... then the gathered source row (staging tile S) and the destination row quarter (staged D block; the rows of a warp
-      //      mostly share it: broadcast reads) are added chunk by chunk
+      f2 x[16];
       mbar_wait(bar(B_S_FULL), ph);
-      {
-        const uint32_t d_row = sD + (uint32_t)d0 * 512u + (uint32_t)qq * 128u;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v = lds128(s_row + 16u * c), w = lds128(d_row + 16u * c);
-          x[2 * c] = add2(x[2 * c], add2(pk2(v.x, v.y), pk2(w.x, w.y)));
-          x[2 * c + 1] = add2(x[2 * c + 1], add2(pk2(v.z, v.w), pk2(w.z, w.w)));
-        }
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = lds128(s_row + 16u * c);
+        x[2 * c] = add2(pk2(v.x, v.y), pk2(av[c].x, av[c].y)); x[2 * c + 1] = add2(pk2(v.z, v.w), pk2(av[c].z, av[c].w));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_S_EMPTY));
+      // ---- + gaussian/type block from the tensor core
+      mbar_wait(bar(B_DPRE_FULL), ph);
+      tc_fence_after();
+      {
+        uint32_t v0[16], v1[16];
+        const uint32_t ta = t_lane + kColDpre + (uint32_t)(32 * qq);
+        tmem_ld16_nowait(ta, v0);
+        tmem_ld16_nowait(ta + 16u, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          x[i] = add2(x[i], pk2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1])));
+          x[8 + i] = add2(x[8 + i], pk2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1])));
+        }
+      }
+      tc_fence_before();
       // ---- gaussians of the NEXT tile now (the small MMA and its round trip overlap this tile's LayerNorm), metadata two ahead
       if (it + 1 < my_tiles) write_g(s1, t1, dist1);
       s0 = s1; t0 = t1; d0 = d1; dist0 = dist1;
       load_md(it + 2, s1, t1, d1, dist1);
+      if (s0 >= 0) prefetch_l1(P + (size_t)d0 * TD_NPROJ + offA + 32 * qq);      // next tile's destination row quarter -> L1
       // ---- LayerNorm over the 128 features of the row: 4 threads (feature quarters) exchange partial sums through smem.
       //      Slot set 0 is rewritten only after every thread passed this tile's second barrier, set 1 only after the next tile's first.
       f2 sa = add2(x[0], x[1]), sb = add2(x[2], x[3]), sc = add2(x[4], x[5]), sd = add2(x[6], x[7]);
@@ -395,29 +400,25 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       named_bar_sync(1 + q, 128);
       const float var = ((lds32f(xslot + 2048u) + lds32f(xslot + 2560u)) + (lds32f(xslot + 3072u) + lds32f(xslot + 3584u))) * (1.0f / 128.0f);
       const float rstd = rsqrtf(var + 1e-5f);
-      // ---- affine + ReLU, bf16 split -> this row's 32 features of both A pieces in tensor memory, 8 features (4 packed columns) at a
-      //      time to keep few registers live.  Absent rows carry x = 0: their (finite) outputs are never consumed.
-      mbar_wait(bar(B_A_EMPTY), ph ^ 1u);         // the previous tile's MMAs have read A
-      tc_fence_after();
+      // ---- affine + ReLU, bf16 split -> this row's 32 features of both A pieces (16 packed columns each) in tensor memory.
+      //      Absent rows carry x = 0: their (finite) outputs are never consumed.
+      uint32_t hi[16], lo[16];
       {
         const f2 rstd2 = pk2(rstd, rstd);
-        const uint32_t ta = t_lane + kColA + (uint32_t)(16 * qq);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float4 g = lds128(sLN + 16u * (uint32_t)(8 * qq + 2 * c + u)), b = lds128(sLN + 512u + 16u * (uint32_t)(8 * qq + 2 * c + u));
-            float y0, y1, y2, y3;
-            upk2(fma2(x[4 * c + 2 * u], mul2(rstd2, pk2(g.x, g.y)), pk2(b.x, b.y)), y0, y1);
-            upk2(fma2(x[4 * c + 2 * u + 1], mul2(rstd2, pk2(g.z, g.w)), pk2(b.z, b.w)), y2, y3);
-            split2(fmaxf(y0, 0.f), fmaxf(y1, 0.f), hi[2 * u], lo[2 * u]);
-            split2(fmaxf(y2, 0.f), fmaxf(y3, 0.f), hi[2 * u + 1], lo[2 * u + 1]);
-          }
-          tmem_st4(ta + 4u * c, hi);
-          tmem_st4(ta + 64u + 4u * c, lo);
+        for (int c = 0; c < 8; ++c) {
+          const float4 g = lp.g4[8 * qq + c], b = lp.b4[8 * qq + c];
+          float y0, y1, y2, y3;
+          upk2(fma2(x[2 * c], mul2(rstd2, pk2(g.x, g.y)), pk2(b.x, b.y)), y0, y1);
+          upk2(fma2(x[2 * c + 1], mul2(rstd2, pk2(g.z, g.w)), pk2(b.z, b.w)), y2, y3);
+          split2(fmaxf(y0, 0.f), fmaxf(y1, 0.f), hi[2 * c], lo[2 * c]);
+          split2(fmaxf(y2, 0.f), fmaxf(y3, 0.f), hi[2 * c + 1], lo[2 * c + 1]);
         }
       }
+      mbar_wait(bar(B_A_EMPTY), ph ^ 1u);         // the previous tile's MMAs have read A
+      tc_fence_after();
+      tmem_st16(t_lane + kColA + (uint32_t)(16 * qq), hi);
+      tmem_st16(t_lane + kColA + 64u + (uint32_t)(16 * qq), lo);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -427,8 +428,9 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
     // ================================================================= gather warps (lane = 4 features), 32 rows each; the last one
     //                                                                   also issues the MMAs (one thread) between its copies
     // Register budget.  The CTA is launched with 72 registers x 896 threads; setmaxnreg only moves registers INSIDE that allocation:
-    // the gather warps must release (72 - 40) x 128 = 4096 so that the row warps' increase of (80 - 72) x 512 = 4096 can be granted
-    // (a smaller release leaves the row warps blocked in setmaxnreg.inc forever).
+    // the gather warps release (72 - 40) x 128 = 4096, exactly what the row warps' increase (80 - 72) x 512 needs (a smaller release
+    // leaves the row warps blocked in setmaxnreg.inc forever).  Local-memory spills are poison here (18 KB of L1 beside 209 KB of
+    // shared memory): measured on B200, variants of this loop with 100+ bytes of spills ran 15-20 % slower than this one (8 bytes).
     reg_dec<40>();
     const int gw = warp - kGatherWarp0;
     const bool mma_warp = warp == kMmaWarp;
@@ -517,20 +519,6 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
           const uint32_t dsta = sS + (uint32_t)atom * kSAtom + (uint32_t)row * kSRow + (uint32_t)(ch << 4);
           if (sr >= 0) cp_async16(dsta, P + (size_t)sr * TD_NPROJ + offB + 4 * lane);
           else sts128f(dsta, make_float4(0.f, 0.f, 0.f, 0.f));
-        }
-        {
-          // ---- the tile's destination rows P[dst, offA + 4*lane ..] -> D (512 B each); absent rows read zeros through S, so padding
-          //      destinations only need defined bytes
-          const long long idx0 = (blockIdx.x + it * (long long)gridDim.x) * 128;
-          int j0;
-          const unsigned a0 = row_dst(idx0, j0);
-          for (int d = gw; d < kDstSlots; d += kGatherWarps) {
-            const long long a = (long long)a0 + d;
-            const int dn = (a < n_dst && a * k < idx0 + 128) ? row_nodes[a] : -1;
-            const uint32_t dsta = sD + (uint32_t)d * 512u + (uint32_t)(lane << 4);
-            if (dn >= 0) cp_async16(dsta, P + (size_t)dn * TD_NPROJ + offA + 4 * lane);
-            else sts128f(dsta, make_float4(0.f, 0.f, 0.f, 0.f));
-          }
         }
         cp_async_wait_all();
         __syncwarp();

@@ -464,7 +464,6 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     else if (!strcmp(mode, "tc6")) e->mlp_mode = 3;
     else { cudaFree(e->arena); cudaFree(e->img_arena); delete e; return set_err(TDIFF_EINVAL, "TDIFF_EDGE_MLP=%s (simt|tc3|tc3v2|tc6)", mode); }
   }
-  if (cfg->knn < 19) e->mlp_v4 = false;          // the v4 edge kernel stages <= 8 destination rows per 128-row tile; tiny k runs the previous kernel
   if ((cfg->ew_net_type != 0 || cfg->x2h_out_fc) && !(e->mlp_mode == 2 && e->mlp_v4)) {
     cudaFree(e->arena); cudaFree(e->img_arena); delete e;
     return set_err(TDIFF_EINVAL, "ew_net_type != 'global' and x2h_out_fc are implemented by the default engine mode only (unset TDIFF_EDGE_MLP)");

@@ -168,14 +168,15 @@ def _best_thread_count(sd, a, b):
     return best
 
 
-def cpu_oracle_rate(a, graphs, steps, warmup=3):
+def cpu_oracle_rate(a, graphs, steps, warmup=3, cores=None):
     """The reference's algorithm on the host cores (oracle/restate.py, torch CPU) on a bounded sample of the same workload:
     `graphs` graphs of the same shape x `steps` denoising steps.  Returns (molecules/s, s/step, info)."""
     import torch
     from oracle import restate, synth
     sd = synth.make_state_dict(0, {'knn': a.knn}, schedules=restate.make_schedules())
     b = synth.make_batch(1, graphs, n_protein=a.n_protein, n_ligand=int(round(a.n_ligand)), distinct_pockets=graphs)
-    cores = _best_thread_count(sd, a, b)
+    if cores is None:
+        cores = _best_thread_count(sd, a, b)
     torch.set_num_threads(cores)
     S = warmup + steps
     pn, vu = synth.make_tape(7, S, len(b['batch_ligand']))
@@ -195,8 +196,10 @@ def cpu_arm(a, steps, warmup=3):
     """CPU arm at every batch size of --cpu-graphs (1 and 16); the best rate is the reported value."""
     best = None
     runs = []
+    cores = None                       # thread count chosen once, on the first (smallest) batch size
     for g in [max(1, int(x)) for x in str(a.cpu_graphs).split(',') if x.strip()]:
-        rate, per_step, info = cpu_oracle_rate(a, g, steps, warmup)
+        rate, per_step, info = cpu_oracle_rate(a, g, steps, warmup, cores)
+        cores = info['cores']
         runs.append({'graphs': g, 'molecules_per_s': rate, 's_per_step': per_step, 'cores': info['cores']})
         if best is None or rate > best[0]:
             best = (rate, per_step, info)

@@ -25,6 +25,13 @@ for w in $what; do
       ncu -i gpurun_out/${tag}_v4.ncu-rep --page raw --csv > gpurun_out/${tag}_v4_raw.csv 2>/dev/null
       ncu -i gpurun_out/${tag}_v4.ncu-rep --page source --csv --print-source sass > gpurun_out/${tag}_v4_source.csv 2>/dev/null
       ncu -i gpurun_out/${tag}_v4.ncu-rep --page source --csv --print-source cuda > gpurun_out/${tag}_v4_source_cuda.csv 2>/dev/null ;;
+    aggh)
+      timeout 300 ncu --set full --clock-control none -k regex:aggregate_h_kernel -s 3 -c 1 -o gpurun_out/${tag}_agg_h python tools/agg_h_standalone.py > gpurun_out/${tag}_agg_h.log 2>&1
+      ncu -i gpurun_out/${tag}_agg_h.ncu-rep --page raw --csv > gpurun_out/${tag}_agg_h_raw.csv 2>/dev/null
+      timeout 120 python tools/agg_h_standalone.py | tail -1 ;;
+    scale2)
+      timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/${tag}_scale_2gpu.json 2> gpurun_out/${tag}_scale_2gpu.err; cut -c1-330 gpurun_out/${tag}_scale_2gpu.json; tail -3 gpurun_out/${tag}_scale_2gpu.err
+      timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 3 --warmup 3 > gpurun_out/${tag}_scale_2gpu_reference.json 2>/dev/null; cut -c1-200 gpurun_out/${tag}_scale_2gpu_reference.json ;;
     audit) timeout 900 python tools/precision_audit.py --out gpurun_out/${tag}_precision_audit.json > gpurun_out/${tag}_audit.log 2>&1; tail -8 gpurun_out/${tag}_audit.log ;;
   esac
 done

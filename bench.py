@@ -429,8 +429,16 @@ def main():
             torch.cuda.synchronize(dev)
             t_u = e0.elapsed_time(e1) / reps * 1e-3
             bytes_u = E * 1028 + N * 1536
+            traffic_u = None             # DRAM bytes of one launch from this round's committed ncu capture of the same problem size
+            try:
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_aggregate_h_traffic.json')))
+                if tj.get('nodes') == N and tj.get('k') == kk:
+                    traffic_u = tj['dram_bytes_per_launch']
+            except Exception:
+                pass
             extra['roofline_unfused_aggregate'] = {'kernel': 'aggregate_h_kernel (tdiff_attn_aggregate_h: keys + values from HBM)', 'bound': 'hbm',
                                                    'achieved': bytes_u / t_u / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': bytes_u / t_u / 1e9 / peak,
+                                                   'traffic': traffic_u,
                                                    'algorithmic_bytes_per_launch': bytes_u, 'avg_launch_ms': t_u * 1e3,
                                                    'note': 'stand-alone operator on random data of the bench problem size; the engine itself fuses the '
                                                            'logits into the key-MLP epilogue (roofline above)'}

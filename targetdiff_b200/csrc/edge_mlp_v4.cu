@@ -41,7 +41,7 @@ constexpr int kTabClassBytes = 2 * kAtom;  // one class table: 2 bf16 pieces of 
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int oW = 0, oG = oW + 4 * kAtom, oT = oG + 2 * kAtom, oS = oT + 2 * kAtom, oX = oS + 4 * kSAtom, oBar = oX + 2 * 2048,
               kSmem = oBar + 16 * 8 + 16;
-enum { B_S_FULL = 0, B_S_EMPTY, B_G_FULL, B_A_FULL, B_A_EMPTY, B_DPRE_FULL, B_D_FULL0, B_D_FULL1, B_D_EMPTY0, B_D_EMPTY1 };
+enum { B_S_FULL = 0, B_S_EMPTY, B_G_FULL, B_A_FULL, B_A_EMPTY, B_DPRE_FULL, B_D_FULL0, B_D_FULL1, B_D_EMPTY0, B_D_EMPTY1, B_LOAD, B_TAB };
 constexpr uint32_t kColD = 0, kColDpre = 256, kColA = 384;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -62,6 +62,14 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     if (done) break;
     __nanosleep(100);
   }
+}
+// TMA bulk copy (1-D): global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP + SYNCS.ARRIVE.TRANS64)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc), "r"(bytes),
+               "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -245,18 +253,9 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
   constexpr int kWAtom = NOUT * 128;            // one K-half of a weight piece: NOUT rows x 128 B
   constexpr int kWPiece = 2 * kWAtom;
   constexpr uint32_t kIdescMain = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
-  for (int i = tid; i < 2 * kWPiece / 16; i += kThreads) {
-    const uint4 v = reinterpret_cast<const uint4*>(w2_image)[i];
-    sts128(sW + 16 * i, v.x, v.y, v.z, v.w);
-  }
-  {
-    const uint4* tsrc = reinterpret_cast<const uint4*>(tab_image + (size_t)tile_class(0) * kTabClassBytes);
-    for (int i = tid; i < kTabClassBytes / 16; i += kThreads) {
-      const uint4 v = tsrc[i];
-      sts128(sT + 16 * i, v.x, v.y, v.z, v.w);
-    }
-  }
   if (tid == 0) {
+    mbar_init(bar(B_LOAD), 1);
+    mbar_init(bar(B_TAB), 1);
     mbar_init(bar(B_S_FULL), kGatherWarps);
     mbar_init(bar(B_S_EMPTY), kRowWarps);
     mbar_init(bar(B_G_FULL), kRowWarps);
@@ -268,6 +267,10 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
     mbar_init(bar(B_D_EMPTY0), kEpiWarps);
     mbar_init(bar(B_D_EMPTY1), kEpiWarps);
     fence_barrier_init();
+    // the two MMA B operands arrive as TMA bulk copies (no registers, no per-thread loops); only the MMA-issuing warp waits for them
+    mbar_expect_tx(bar(B_LOAD), 2u * kWPiece + (uint32_t)kTabClassBytes);
+    bulk_g2s(sW, w2_image, 2u * kWPiece, bar(B_LOAD));
+    bulk_g2s(sT, tab_image + (size_t)tile_class(0) * kTabClassBytes, (uint32_t)kTabClassBytes, bar(B_LOAD));
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(s_tmem), 512);
   fence_proxy_async();
@@ -455,13 +458,13 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       mbar_wait(bar(B_G_FULL), (uint32_t)(t & 1));       // every row warp has written G(t), i.e. has also read Dpre(t-1): sT is idle
       tc_fence_after();
       const int cls = tile_class(t);
-      if (cls != cur_class) {                            // at most once per CTA and launch (tiles are class-sorted)
-        const uint4* tsrc = reinterpret_cast<const uint4*>(tab_image + (size_t)cls * kTabClassBytes);
-        for (int i = lane; i < kTabClassBytes / 16; i += 32) {
-          const uint4 v = tsrc[i];
-          sts128(sT + 16 * i, v.x, v.y, v.z, v.w);
+      if (t == 0) mbar_wait(bar(B_LOAD), 0);              // W2 pieces and the first class table have landed
+      if (cls != cur_class) {                            // at most once per CTA and launch (tiles are class-sorted): swap the table by TMA
+        if (lane == 0) {
+          mbar_expect_tx(bar(B_TAB), (uint32_t)kTabClassBytes);
+          bulk_g2s(sT, tab_image + (size_t)cls * kTabClassBytes, (uint32_t)kTabClassBytes, bar(B_TAB));
         }
-        fence_proxy_async();
+        mbar_wait(bar(B_TAB), 0);
         cur_class = cls;
         __syncwarp();
       }

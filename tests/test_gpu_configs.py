@@ -294,3 +294,22 @@ def test_experimental_slow_tc_vs_oracle(monkeypatch):
     got = model.sample_diffusion(*_args(b), num_steps=S, center_pos_mode='protein', noise_tape=(pn, vu))
     assert torch.equal(torch.stack(got['v_traj']), torch.stack(want['v_traj']))
     torch.testing.assert_close(torch.stack(got['pos_traj']), torch.stack(want['pos_traj']), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs in one process')
+def test_two_engines_two_devices_one_process():
+    """One process may own an engine on every GPU (kernel attributes such as the dynamic shared-memory opt-in are per device:
+    round-1 advisor finding).  The same chain on cuda:0 and cuda:1 must give identical results."""
+    from targetdiff_b200.config import default_model_config
+    from targetdiff_b200.score_model import ScorePosNet3D
+    b = synth.make_batch(4, 2, n_protein=80, ligand_sizes=[10, 6])
+    pn, vu = synth.make_tape(2, 4, 16)
+    outs = []
+    for dev in ('cuda:0', 'cuda:1'):
+        m = ScorePosNet3D(default_model_config(), synth.PROTEIN_FEATURE_DIM, synth.LIGAND_NUM_CLASSES)
+        m.load_state_dict(synth.make_state_dict(0, schedules=restate.make_schedules()), strict=True)
+        m = m.to(dev)
+        with torch.cuda.device(dev):
+            r = m.sample_diffusion(*_args(b, dev), num_steps=4, center_pos_mode='protein', noise_tape=(pn, vu), stack_traj=True)
+        outs.append((r['pos'].cpu(), r['pos_traj'], r['v_traj'], m))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])

@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument('--n-ligand', type=int)
     ap.add_argument('--knn', type=int)
     ap.add_argument('--full-chain', action='store_true', help='time one real 1000-step chain (overrides --steps)')
-    ap.add_argument('--e2e-steps', type=int, default=50, help='denoising steps per end-to-end public-API call')
+    ap.add_argument('--e2e-steps', type=int, default=100, help='denoising steps per end-to-end public-API call')
     ap.add_argument('--profile-steps', type=int, default=3, help='eager steps timed per kernel with CUDA events for the roofline')
     ap.add_argument('--cpu-graphs', type=str, default='1,16', help='batch sizes of the CPU arm (BASELINE.md section 3: 1 and 16)')
     ap.add_argument('--cpu-steps', type=int, default=3)

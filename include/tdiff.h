@@ -60,7 +60,11 @@ typedef struct tdiff_config {
   int32_t x2h_out_fc;        /* 1: node_output MLP on [aggregate | h] before the residual (:39-40,80-81) */
   int32_t time_emb;          /* 0: time_emb_dim = 0; 1: time_emb_mode 'simple', one extra ligand input column time_step / T
                               * (models/molopt_score_model.py:319-324); 'sin' cannot run in the reference itself (:325-326) */
-  int32_t reserved[3];       /* must be 0 */
+  int32_t cutoff_mode;       /* 0 'knn' (models/uni_transformer.py:279-280); 1 'hybrid' (:281-283 -> models/common.py:165-212, add_p_index):
+                              * a ligand destination gets every other ligand atom of its graph + its knn nearest protein atoms, protein
+                              * destinations keep the k-NN over all atoms.  Needs knn + max ligand atoms per graph - 1 <= 64 slots and
+                              * >= knn protein atoms per graph (checked at tdiff_bind_batch).  'radius' is a dead path in the reference */
+  int32_t reserved[2];       /* must be 0 */
 } tdiff_config;
 
 /* One state_dict entry (reference key name, fp32, host memory).  SURVEY.md Appendix D lists the 384 keys. */

@@ -186,6 +186,38 @@ def knn_graph_canonical(x, k, batch):
     return torch.from_numpy(np.stack([src, dst]).astype(np.int64))
 
 
+def hybrid_graph(x, k, mask_ligand, batch):
+    """cutoff_mode='hybrid' (models/uni_transformer.py:281-283 -> models/common.py:165-212, add_p_index=True).  Per graph, in this
+    edge order: ligand-ligand fully connected (dst-major, :167-171), for every ligand atom its k nearest PROTEIN atoms by
+    torch.norm distance / torch.topk (:174-182), and for protein destinations the ordinary k-NN over all atoms of the graph
+    (:196-203; nodes of a graph are protein atoms then ligand atoms after compose_context, so `all_index` is the identity)."""
+    B = int(batch.max().item()) + 1 if len(batch) else 0
+    out = []
+    for g in range(B):
+        lig = ((batch == g) & (mask_ligand == 1)).nonzero()[:, 0]                       # :190
+        pro = ((batch == g) & (mask_ligand == 0)).nonzero()[:, 0]                       # :191
+        dst = torch.repeat_interleave(lig, len(lig))                                    # :167
+        src = lig.repeat(len(lig))                                                      # :168
+        keep = dst != src
+        ll = torch.stack([src[keep], dst[keep]])
+        d = torch.norm(x[lig].unsqueeze(1) - x[pro].unsqueeze(0), p=2, dim=-1)         # :174-175
+        nn_p = pro[torch.topk(d, k=k, largest=False, dim=1).indices]                    # :176-177
+        pl = torch.stack([nn_p, lig.unsqueeze(1).repeat(1, k)], 0).view(2, -1)         # :178-182
+        nodes = torch.cat([pro, lig])
+        pe = knn_graph_canonical(x[nodes], k, torch.zeros(len(nodes), dtype=torch.long))   # :197
+        pe = pe[:, pe[1] < len(pro)]                                                    # :198
+        pe = torch.stack([nodes[pe[0]], nodes[pe[1]]], 0)                               # :199-202
+        out.append(torch.cat([ll, pl, pe], -1))                                         # :205-206
+    return torch.cat(out, -1) if out else torch.zeros(2, 0, dtype=torch.long)
+
+
+def connect_edge(x, cfg, mask_ligand, batch):
+    """_connect_edge (models/uni_transformer.py:276-286); 'radius' is a dead path in the reference (undefined self.r)."""
+    if cfg['cutoff_mode'] == 'hybrid':
+        return hybrid_graph(x, cfg['knn'], mask_ligand, batch)
+    return knn_graph_canonical(x, cfg['knn'], batch)
+
+
 def build_edge_type(edge_index, mask_ligand):
     """uni_transformer.py:288-299: L->L 0, L(src)->P(dst) 1, P(src)->L(dst) 2, P->P 3; one-hot int64 [E,4]."""
     src, dst = edge_index
@@ -284,10 +316,10 @@ def att_layer(sd, prefix, h, x, edge_type, edge_index, mask_ligand, e_w, n_heads
 def refine_net(sd, cfg, h, x, mask_ligand, batch, fix_x=False, edge_index=None, trace=None):
     """UniTransformerO2TwoUpdateGeneral.forward (uni_transformer.py:301-328): num_blocks x (k-NN graph, edge types, optional global
     gate, the SAME num_layers attention layers)."""
-    assert cfg['cutoff_mode'] == 'knn' and cfg['ew_net_type'] in ('global', 'r', 'm', 'none')
+    assert cfg['cutoff_mode'] in ('knn', 'hybrid') and cfg['ew_net_type'] in ('global', 'r', 'm', 'none')
     given = edge_index
     for b in range(cfg['num_blocks']):                                                   # :306
-        edge_index = given if (given is not None and b == 0) else knn_graph_canonical(x, cfg['knn'], batch)   # :307
+        edge_index = given if (given is not None and b == 0) else connect_edge(x, cfg, mask_ligand, batch)   # :307
         src, dst = edge_index
         edge_type = build_edge_type(edge_index, mask_ligand)                             # :311
         e_w = None

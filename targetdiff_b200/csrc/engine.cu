@@ -89,6 +89,9 @@ struct tdiff_engine {
   // developer switches, read from the environment ONCE in tdiff_create (never on the per-layer path)
   bool env_no_fused_agg = false, env_no_restrict = false, env_no_graph = false, env_knn_full = false, env_no_slot_keep = false;
   int B = 0, N = 0, Np = 0, Nl = 0, K = 0, max_ng = 0, final_buf = 0;
+  // cutoff_mode 'hybrid': KQ = the configured k (neighbours searched), K = slots per row = KQ + max ligand atoms per graph - 1 (set at
+  // bind time); 'knn': K == KQ
+  int KQ = 0, hybrid = 0;
   DevBuf node_ptr, prot_ptr, prot_node, prot_graph, lig_node, lig_graph, node_lig;
   DevBuf rel_flag, rel_list, n_rel, work_list, n_work, knn_cache;
   // class-sorted destination lists of the v4 edge kernel: protein destinations (padded with -1 to `row_pad`), then ligand destinations
@@ -341,6 +344,7 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     return set_err(TDIFF_EINVAL, "model_mean_type=%d (0 = C0, 1 = noise)", cfg->model_mean_type);
   for (int r : cfg->reserved)
     if (r != 0) return set_err(TDIFF_EINVAL, "tdiff_config.reserved must be 0");
+  if (cfg->cutoff_mode != 0 && cfg->cutoff_mode != 1) return set_err(TDIFF_EINVAL, "cutoff_mode=%d (0 = 'knn', 1 = 'hybrid')", cfg->cutoff_mode);
   if (cfg->num_blocks < 0 || cfg->num_blocks > 16 || cfg->ew_net_type < 0 || cfg->ew_net_type > 3 || (cfg->x2h_out_fc != 0 && cfg->x2h_out_fc != 1) ||
       (cfg->time_emb != 0 && cfg->time_emb != 1))
     return set_err(TDIFF_EINVAL, "bad option (num_blocks=%d ew_net_type=%d x2h_out_fc=%d time_emb=%d)", cfg->num_blocks, cfg->ew_net_type,
@@ -360,7 +364,7 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
   if (prop.major < 10) return set_err(TDIFF_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
 
   tdiff_engine* e = new tdiff_engine();
-  e->cfg = *cfg; e->device = device; e->sm_count = prop.multiProcessorCount; e->K = cfg->knn;
+  e->cfg = *cfg; e->device = device; e->sm_count = prop.multiProcessorCount; e->K = e->KQ = cfg->knn; e->hybrid = cfg->cutoff_mode;
   e->num_blocks = cfg->num_blocks > 1 ? cfg->num_blocks : 1; e->ew_mode = cfg->ew_net_type; e->out_fc = cfg->x2h_out_fc; e->time_emb = cfg->time_emb;
 
   Packer pk;
@@ -550,6 +554,20 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   }
   N = Np + Nl;
   if (N <= 0) return set_err(TDIFF_EINVAL, "empty batch");
+  if (e->hybrid) {
+    // reference models/common.py:165-212: a ligand destination has (n_ligand - 1) ligand neighbours + k protein neighbours (torch.topk
+    // raises when a graph has fewer than k protein atoms); the slot rows are sized for the largest ligand of the batch
+    int max_lc = 0;
+    for (int g = 0; g < B; ++g) {
+      if (lc[g] > max_lc) max_lc = lc[g];
+      if (lc[g] > 0 && pc[g] < e->KQ)
+        return set_err(TDIFF_EINVAL, "cutoff_mode 'hybrid': graph %d has %d protein atoms < k = %d (torch.topk fails in the reference too)", g, pc[g], e->KQ);
+    }
+    const int need = e->KQ + (max_lc > 0 ? max_lc - 1 : 0);
+    if (need > TD_KMAX)
+      return set_err(TDIFF_EINVAL, "cutoff_mode 'hybrid': k + n_ligand - 1 = %d + %d - 1 exceeds the %d neighbour slots per node", e->KQ, max_lc, TD_KMAX);
+    e->K = need;
+  }
   if (N * (long long)e->K >= (1LL << 31) / 1) return set_err(TDIFF_EINVAL, "batch too large: N*k = %lld edge slots", N * e->K);
   if (max_ng > 2800) return set_err(TDIFF_EINVAL, "graph with %d nodes exceeds the k-NN kernel's shared-memory tile (2800)", max_ng);
   if (Np > 0 && (!d_ppos || !d_pfeat)) return set_err(TDIFF_EINVAL, "null protein arrays");
@@ -597,7 +615,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   int min_pc = 1 << 30;
   for (int g = 0; g < B; ++g) if (pc[g] < min_pc) min_pc = pc[g];
   e->free_ready = false;
-  e->free_depth = (fuse && Nl > 0 && min_pc > K) ? e->env_free_depth : 0;      // (only block 0 of a multi-block network uses it)
+  e->free_depth = (fuse && !e->hybrid && Nl > 0 && min_pc > K) ? e->env_free_depth : 0;      // (only block 0 of a multi-block network uses it)
   if (e->free_depth > (int)e->layers.size() - 1) e->free_depth = (int)e->layers.size() - 1;
   if (e->free_depth > 0)
     bad |= e->h_free.ensure((size_t)e->free_depth * N * TD_H * 4) | e->dirty.ensure((size_t)e->free_depth * N + 16) |
@@ -607,7 +625,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   bad |= e->lig_pos.ensure(Nl * 16 + 16) | e->lig_v.ensure(Nl * 4 + 4) | e->logits.ensure((size_t)Nl * e->cfg.num_classes * 4 + 4);
   bad |= e->node_off.ensure(N * 8) | e->rel_flag.ensure(N + 16) | e->rel_list.ensure(N * 4 + 64) | e->n_rel.ensure(16) | e->work_list.ensure(N * 4 + 64) | e->n_work.ensure(16);
   e->knn_incremental = !e->env_knn_full && Np > 0;
-  if (e->knn_incremental) bad |= e->knn_cache.ensure((size_t)N * (K + 1) * 8);
+  if (e->knn_incremental) bad |= e->knn_cache.ensure((size_t)N * (e->KQ + 1) * 8);
   if (bad) return set_err(TDIFF_ECUDA, "out of device memory binding a batch of %lld nodes (%zu edge slots)", N, slots);
   CK(cudaMemcpyAsync(e->node_ptr.p, node_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->prot_ptr.p, prot_ptr.data(), (B + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -637,7 +655,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   td_launch_protein_embed(d_pfeat, (int)Np, e->cfg.protein_feat_dim, e->w_prot, e->b_prot, e->prot_node.as<int>(), e->h0.as<float>(), st);
   e->launches += 3;
   if (e->knn_incremental) {      // protein atoms never move: their protein-only neighbour keys are computed once per bound batch
-    td_launch_knn_cache(e->xm0.as<float4>(), e->node_ptr.as<int>(), e->prot_ptr.as<int>(), B, max_ng, K, e->knn_cache.as<unsigned long long>(), st);
+    td_launch_knn_cache(e->xm0.as<float4>(), e->node_ptr.as<int>(), e->prot_ptr.as<int>(), B, max_ng, e->KQ, e->knn_cache.as<unsigned long long>(), st);
     e->launches += 1;
   }
   CK(cudaGetLastError());
@@ -768,9 +786,10 @@ void run_forward(tdiff_engine* e, cudaStream_t st, int fix_x, int free_build = 0
     const int use_free = (!free_build && e->free_ready && blk == 0) ? e->free_depth : 0;
     const bool last_blk = blk + 1 == n_blocks;
     if (e->knn_incremental)
-      td_launch_knn_update(xm[cur], e->node_ptr.as<int>(), e->prot_ptr.as<int>(), e->B, e->max_ng, K, e->knn_cache.as<unsigned long long>(), e->src.as<int>(), st);
+      td_launch_knn_update(xm[cur], e->node_ptr.as<int>(), e->prot_ptr.as<int>(), e->B, e->max_ng, e->KQ, K, e->hybrid, e->knn_cache.as<unsigned long long>(),
+                           e->src.as<int>(), st);
     else
-      td_launch_knn(xm[cur], e->node_ptr.as<int>(), e->B, e->max_ng, K, e->src.as<int>(), st);
+      td_launch_knn(xm[cur], e->node_ptr.as<int>(), e->prot_ptr.as<int>(), e->B, e->max_ng, e->KQ, K, e->hybrid, e->src.as<int>(), st);
     td_launch_edge_const(xm[cur], src, e->src_prev.as<int>(), e->have_prev ? 1 : 0, N, K, e->ew_off, e->ew_coeff, e->ew_w1t, e->ew_b1, e->ew_g, e->ew_b, e->ew_w2,
                          e->ew_b2, e->etype.as<unsigned char>(), e->e_w.as<float>(), e->rel_flag.as<unsigned char>(),
                          use_free ? e->dirty.as<unsigned char>() : nullptr, e->work_list.as<int>(), e->n_work.as<int>(), (e->ew_mode != 0 ? 1 : 0) | (e->env_no_slot_keep ? 2 : 0), st);
@@ -1135,7 +1154,7 @@ extern "C" int tdiff_knn_graph(const float* d_x, int n_nodes, const int32_t* h_c
   } else {
     cudaMemcpyAsync(dptr.p, ptr.data(), (n_graphs + 1) * 4, cudaMemcpyHostToDevice, st);
     td_launch_pack_xyzm(d_x, nullptr, n_nodes, xm.as<float4>(), st);
-    td_launch_knn(xm.as<float4>(), dptr.as<int>(), n_graphs, max_ng, k, d_src_slots, st);
+    td_launch_knn(xm.as<float4>(), dptr.as<int>(), nullptr, n_graphs, max_ng, k, k, 0, d_src_slots, st);
     td_launch_edge_count_scan(d_src_slots, n_nodes, k, off.as<long long>(), tot.as<long long>(), st);
     if (d_edge_index) td_launch_edge_compact(d_src_slots, nullptr, n_nodes, k, off.as<long long>(), tot.as<long long>(), (long long*)d_edge_index, nullptr, st);
     long long t = 0;

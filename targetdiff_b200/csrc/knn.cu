@@ -7,6 +7,11 @@
 // The (d2, index) order is realised with one 64-bit key  (float_as_uint(d2) << 32) | local_index : d2 >= 0 so the
 // IEEE bit pattern is monotone, keys are unique, and "k+1 smallest keys" is exactly the canonical selection.
 //
+// cutoff_mode = 'hybrid' (reference models/common.py:165-212, add_p_index=True): protein destinations keep the k-NN over all atoms of
+// the graph; a ligand destination gets every other ligand atom of its graph (ascending node index) followed by its k nearest PROTEIN
+// atoms (same key order; the reference ranks torch.norm distances with torch.topk).  Rows have `stride` >= k slots (the engine uses
+// stride = k + max ligand atoms per graph - 1); unused slots are -1.
+//
 // Mapping: one CTA per (graph, chunk of queries); the graph's coordinates are staged once in shared memory
 // (coalesced float4 loads); one warp per query holds the key row in shared memory, each lane tracks the minimum of
 // its strided slice; k+1 rounds of a 64-bit warp-min pick the neighbours in order, only the winning lane rescans.
@@ -23,8 +28,50 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
   return v;
 }
 
+// One hybrid ligand row (warp-collective): other ligand atoms of the graph, then the k nearest protein atoms; `keys` = this warp's
+// shared-memory key row, `spos` = the graph's staged coordinates (protein atoms first).
+__device__ __forceinline__ void hybrid_ligand_row(const float4* spos, unsigned long long* keys, int qi, int np, int ng, int k, int stride, int base,
+                                                  int lane, int* out) {
+  const int nl = ng - np;
+  for (int j = lane; j < nl; j += 32) {
+    const int node = np + j;
+    if (node != qi) out[j - (node > qi ? 1 : 0)] = base + node;
+  }
+  const float4 xq = spos[qi];
+  unsigned long long lmin = ~0ull;
+  for (int j = lane; j < np; j += 32) {
+    const float4 xc = spos[j];
+    const float dx = __fsub_rn(xq.x, xc.x), dy = __fsub_rn(xq.y, xc.y), dz = __fsub_rn(xq.z, xc.z);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)j;
+    keys[j] = key;
+    lmin = key < lmin ? key : lmin;
+  }
+  __syncwarp();
+  const int rounds = min(k, np);
+  int written = nl - 1;
+  for (int r = 0; r < rounds && written < stride; ++r) {
+    const unsigned long long gmin = warp_min_u64(lmin);
+    const int j = (int)(gmin & 0xffffffffu);
+    if (lmin == gmin) {
+      keys[j] = ~0ull;
+      unsigned long long m = ~0ull;
+      for (int jj = lane; jj < np; jj += 32) {
+        const unsigned long long kv = keys[jj];
+        m = kv < m ? kv : m;
+      }
+      lmin = m;
+    }
+    if (lane == 0) out[written] = base + j;
+    ++written;
+  }
+  for (int w = written + lane; w < stride; w += 32) out[w] = -1;
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(KNN_WARPS * 32)
-knn_kernel(const float4* __restrict__ xm, const int* __restrict__ node_ptr, int k, int max_ng, int* __restrict__ src) {
+knn_kernel(const float4* __restrict__ xm, const int* __restrict__ node_ptr, const int* __restrict__ prot_ptr, int k, int stride, int hybrid,
+           int max_ng, int* __restrict__ src) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* spos = reinterpret_cast<float4*>(smem_raw);                                     // [max_ng]
   unsigned long long* skeys = reinterpret_cast<unsigned long long*>(spos + max_ng);       // [KNN_WARPS][max_ng]
@@ -32,6 +79,7 @@ knn_kernel(const float4* __restrict__ xm, const int* __restrict__ node_ptr, int 
   const int g = blockIdx.x;
   const int base = node_ptr[g];
   const int ng = node_ptr[g + 1] - base;
+  const int np_h = hybrid ? prot_ptr[g + 1] - prot_ptr[g] : ng;          // hybrid: nodes >= np_h are ligand atoms
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int j = threadIdx.x; j < ng; j += blockDim.x) spos[j] = xm[base + j];
   __syncthreads();
@@ -40,6 +88,10 @@ knn_kernel(const float4* __restrict__ xm, const int* __restrict__ node_ptr, int 
   const int rounds = min(k + 1, ng);
   // queries of this graph are spread over gridDim.y chunks and the CTA's warps
   for (int qi = blockIdx.y * KNN_WARPS + warp; qi < ng; qi += gridDim.y * KNN_WARPS) {
+    if (qi >= np_h) {
+      hybrid_ligand_row(spos, keys, qi, np_h, ng, k, stride, base, lane, src + (size_t)(base + qi) * stride);
+      continue;
+    }
     const float4 xq = spos[qi];
     unsigned long long lmin = ~0ull;
     for (int j = lane; j < ng; j += 32) {
@@ -51,7 +103,7 @@ knn_kernel(const float4* __restrict__ xm, const int* __restrict__ node_ptr, int 
       lmin = key < lmin ? key : lmin;
     }
     __syncwarp();
-    int* out = src + (size_t)(base + qi) * k;
+    int* out = src + (size_t)(base + qi) * stride;
     int written = 0;
     for (int r = 0; r < rounds; ++r) {
       const unsigned long long gmin = warp_min_u64(lmin);
@@ -70,7 +122,7 @@ knn_kernel(const float4* __restrict__ xm, const int* __restrict__ node_ptr, int 
         ++written;
       }
     }
-    for (int w = written + lane; w < k; w += 32) out[w] = -1;
+    for (int w = written + lane; w < stride; w += 32) out[w] = -1;
     __syncwarp();
   }
 }
@@ -130,8 +182,8 @@ knn_protein_cache_kernel(const float4* __restrict__ xm, const int* __restrict__ 
 }
 
 __global__ void __launch_bounds__(KNN_WARPS * 32)
-knn_update_kernel(const float4* __restrict__ xm, const int* __restrict__ node_ptr, const int* __restrict__ prot_ptr, int k, int max_ng,
-                  const unsigned long long* __restrict__ cache, int* __restrict__ src) {
+knn_update_kernel(const float4* __restrict__ xm, const int* __restrict__ node_ptr, const int* __restrict__ prot_ptr, int k, int stride, int hybrid,
+                  int max_ng, const unsigned long long* __restrict__ cache, int* __restrict__ src) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* spos = reinterpret_cast<float4*>(smem_raw);
   unsigned long long* skeys = reinterpret_cast<unsigned long long*>(spos + max_ng);
@@ -145,7 +197,11 @@ knn_update_kernel(const float4* __restrict__ xm, const int* __restrict__ node_pt
   unsigned long long* keys = skeys + (size_t)warp * max_ng;
   for (int qi = blockIdx.y * KNN_WARPS + warp; qi < ng; qi += gridDim.y * KNN_WARPS) {
     const float4 xq = spos[qi];
-    int* out = src + (size_t)(base + qi) * k;
+    int* out = src + (size_t)(base + qi) * stride;
+    if (qi >= np && hybrid) {
+      hybrid_ligand_row(spos, keys, qi, np, ng, k, stride, base, lane, out);
+      continue;
+    }
     if (qi < np) {
       // ---- protein query: cached protein keys + this step's ligand keys, selection by rank counting
       const int m = min(k + 1, np), n = m + (ng - np);
@@ -180,7 +236,7 @@ knn_update_kernel(const float4* __restrict__ xm, const int* __restrict__ node_pt
         if (e0 == 0) {
           int written = top - (rs < top ? 1 : 0);                                   // self is always a candidate (cached at d2 = 0)
           if (written > k) written = k;
-          for (int w = written + lane; w < k; w += 32) out[w] = -1;
+          for (int w = written + lane; w < stride; w += 32) out[w] = -1;
         }
       }
       __syncwarp();
@@ -216,7 +272,7 @@ knn_update_kernel(const float4* __restrict__ xm, const int* __restrict__ node_pt
         ++written;
       }
     }
-    for (int w = written + lane; w < k; w += 32) out[w] = -1;
+    for (int w = written + lane; w < stride; w += 32) out[w] = -1;
     __syncwarp();
   }
 }
@@ -239,17 +295,18 @@ void td_launch_knn_cache(const float4* xm, const int* node_ptr, const int* prot_
   knn_protein_cache_kernel<<<grid, KNN_WARPS * 32, smem, st>>>(xm, node_ptr, prot_ptr, k, max_ng, cache);
 }
 
-void td_launch_knn_update(const float4* xm, const int* node_ptr, const int* prot_ptr, int n_graphs, int max_ng, int k,
+void td_launch_knn_update(const float4* xm, const int* node_ptr, const int* prot_ptr, int n_graphs, int max_ng, int k, int stride, int hybrid,
                           const unsigned long long* cache, int* src, cudaStream_t st) {
   if (n_graphs <= 0) return;
   dim3 grid; size_t smem;
   knn_grid(n_graphs, max_ng, grid, smem);
   static size_t opted[TD_MAX_DEVICES] = {0};
   if (smem > 48 * 1024) td_opt_in_smem(knn_update_kernel, smem, opted);
-  knn_update_kernel<<<grid, KNN_WARPS * 32, smem, st>>>(xm, node_ptr, prot_ptr, k, max_ng, cache, src);
+  knn_update_kernel<<<grid, KNN_WARPS * 32, smem, st>>>(xm, node_ptr, prot_ptr, k, stride, hybrid, max_ng, cache, src);
 }
 
-void td_launch_knn(const float4* xm, const int* node_ptr, int n_graphs, int max_ng, int k, int* src, cudaStream_t st) {
+void td_launch_knn(const float4* xm, const int* node_ptr, const int* prot_ptr, int n_graphs, int max_ng, int k, int stride, int hybrid, int* src,
+                   cudaStream_t st) {
   if (n_graphs <= 0) return;
   size_t smem = (size_t)max_ng * sizeof(float4) + (size_t)KNN_WARPS * max_ng * sizeof(unsigned long long);
   static size_t opted[TD_MAX_DEVICES] = {0};
@@ -259,5 +316,5 @@ void td_launch_knn(const float4* xm, const int* node_ptr, int n_graphs, int max_
   if (chunks < 1) chunks = 1;
   if ((long long)n_graphs * chunks > 65535LL * 8) chunks = 1;
   dim3 grid(n_graphs, chunks);
-  knn_kernel<<<grid, KNN_WARPS * 32, smem, st>>>(xm, node_ptr, k, max_ng, src);
+  knn_kernel<<<grid, KNN_WARPS * 32, smem, st>>>(xm, node_ptr, prot_ptr, k, stride, hybrid, max_ng, src);
 }

@@ -251,7 +251,7 @@ class ScorePosNet3D(nn.Module):
                                 self.num_classes, self.protein_atom_feature_dim, self.num_timesteps,
                                 {'C0': 0, 'noise': 1}[self.model_mean_type], int(self.config.num_blocks),
                                 {'global': 0, 'r': 1, 'm': 2, 'none': 3}[self.config.ew_net_type], int(bool(self.config.x2h_out_fc)),
-                                1 if self.time_emb_dim > 0 else 0)
+                                1 if self.time_emb_dim > 0 else 0, {'knn': 0, 'hybrid': 1}[self.config.get('cutoff_mode', 'knn')])
         out = ctypes.c_void_p()
         _lib.check(lib.tdiff_create(ctypes.byref(cfg), entries, len(sd), index, ctypes.byref(out)))
         self._engine, self._engine_device, self._bound_key = out, index, None

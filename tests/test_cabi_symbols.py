@@ -56,7 +56,7 @@ def test_state_dict_layout_and_unsupported_configs():
     sched = restate.make_schedules()
     assert all(torch.equal(sd[k], sched[k]) for k in synth.SCHEDULE_KEYS)
     m.load_state_dict(synth.make_state_dict(0, schedules=sched), strict=True)
-    for bad in ({'cutoff_mode': 'radius'}, {'cutoff_mode': 'hybrid'}, {'model_type': 'egnn'}, {'time_emb_dim': 8, 'time_emb_mode': 'sin'},
+    for bad in ({'cutoff_mode': 'radius'}, {'model_type': 'egnn'}, {'time_emb_dim': 8, 'time_emb_mode': 'sin'},
                 {'num_blocks': 0}, {'hidden_dim': 256}, {'ew_net_type': 'x'}):
         c = default_model_config()
         c.update(bad)
@@ -64,7 +64,7 @@ def test_state_dict_layout_and_unsupported_configs():
             ScorePosNet3D(c, 27, 13)
     # the backbone options of SURVEY 8(f) n2 are accepted and give the reference's state_dict layout (key order and shapes)
     for opt in ({'num_blocks': 2}, {'ew_net_type': 'r'}, {'ew_net_type': 'm'}, {'ew_net_type': 'none'}, {'x2h_out_fc': True},
-                {'time_emb_dim': 1, 'time_emb_mode': 'simple'}):
+                {'time_emb_dim': 1, 'time_emb_mode': 'simple'}, {'cutoff_mode': 'hybrid'}):
         c = default_model_config()
         c.update(opt)
         m = ScorePosNet3D(c, 27, 13)

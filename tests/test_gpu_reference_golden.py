@@ -244,3 +244,70 @@ def test_backbone_options_vs_oracle(cfgd):
     assert torch.equal(torch.stack(got['v_traj']), torch.stack(w['v_traj']))
     torch.testing.assert_close(torch.stack(got['pos_traj']), torch.stack(w['pos_traj']), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(torch.stack(got['v0_traj']), torch.stack(w['v0_traj']), rtol=0, atol=1e-3)
+
+
+def _sorted_edges(ei):
+    """edge_index as a canonical [E,2] (dst, src) list: the hybrid graph of the reference is emitted per graph as [ligand-ligand |
+    ligand<-protein | protein k-NN] (models/common.py:205-206), the engine's slot list is destination-sorted; the edge SET is what
+    must agree bit for bit."""
+    key = ei[1] * (int(ei.max()) + 1 if ei.numel() else 1) + ei[0]
+    return ei[:, torch.argsort(key)]
+
+
+HYBRID_CONFIGS = [{'cutoff_mode': 'hybrid'}, {'cutoff_mode': 'hybrid', 'knn': 8, 'num_blocks': 2},
+                  {'cutoff_mode': 'hybrid', 'knn': 21, 'ew_net_type': 'r'}]
+
+
+@pytest.mark.parametrize('cfgd', HYBRID_CONFIGS, ids=lambda c: ','.join('%s=%s' % kv for kv in c.items()))
+def test_hybrid_cutoff_vs_oracle(cfgd):
+    """SURVEY 8(f) n2, cutoff_mode='hybrid' (reference models/uni_transformer.py:281-283 -> models/common.py:165-212): every ligand atom
+    is connected to all other ligand atoms of its graph and to its k nearest protein atoms, protein destinations keep the k-NN over all
+    atoms.  Forward and a 6-step chain against the oracle (bit-exact against the unmodified reference for the same configurations,
+    tests/test_oracle_vs_reference.py::test_backbone_options_restatement_bit_exact); slot rows = k + 12 - 1 (43 / 19 / 32: the last one
+    also takes the fused-aggregation path of the edge kernel)."""
+    torch.set_num_threads(16)
+    model, sd = _model(2, cfgd)
+    b = synth.make_batch(9, 3, n_protein=70, ligand_sizes=[12, 5, 9])
+    pp, lp, _ = restate.center_pos(b['protein_pos'], b['init_ligand_pos'], b['batch_protein'], b['batch_ligand'])
+    tr = {}
+    want = restate.forward(sd, cfgd, pp, b['protein_v'], b['batch_protein'], lp, b['init_ligand_v'], b['batch_ligand'], trace=tr)
+    out = model(pp.to(DEV), b['protein_v'].to(DEV), b['batch_protein'].to(DEV), lp.to(DEV), b['init_ligand_v'].to(DEV), b['batch_ligand'].to(DEV))
+    got_ei, want_ei = out['edge_index'].cpu(), tr['block_edge_index'][-1]
+    assert got_ei.shape == want_ei.shape
+    assert torch.equal(_sorted_edges(got_ei), _sorted_edges(want_ei))
+    k = cfgd.get('knn', 32)
+    nodes = 70 * 3 + 26
+    is_lig = torch.zeros(nodes, dtype=torch.bool)
+    start = 0
+    for n_l in (12, 5, 9):
+        is_lig[start + 70:start + 70 + n_l] = True
+        start += 70 + n_l
+    deg = torch.bincount(got_ei[1], minlength=nodes)
+    assert torch.equal(deg[~is_lig], torch.full((210,), k))                      # protein destinations: k-NN over all atoms
+    assert sorted(set(deg[is_lig].tolist())) == sorted({k + 11, k + 4, k + 8})   # ligand destinations: n_l - 1 + k
+    torch.testing.assert_close(out['pred_ligand_pos'].cpu(), want['pred_ligand_pos'], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out['pred_ligand_v'].cpu(), want['pred_ligand_v'], rtol=0, atol=1e-3)
+    torch.testing.assert_close(out['final_h'].cpu(), want['final_h'], rtol=1e-4, atol=1e-4)
+    S = 6
+    pn, vu = synth.make_tape(4, S, len(b['batch_ligand']))
+    w = restate.sample_diffusion(sd, cfgd, *_args(b, 'cpu'), pn, vu, num_steps=S)
+    got = model.sample_diffusion(*_args(b), num_steps=S, center_pos_mode='protein', noise_tape=(pn, vu))
+    assert torch.equal(torch.stack(got['v_traj']), torch.stack(w['v_traj']))
+    torch.testing.assert_close(torch.stack(got['pos_traj']), torch.stack(w['pos_traj']), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(torch.stack(got['v0_traj']), torch.stack(w['v0_traj']), rtol=0, atol=1e-3)
+
+
+def test_hybrid_cutoff_rejects_what_does_not_fit():
+    """k + n_ligand - 1 neighbour slots must fit the 64-slot rows, and every graph needs >= k protein atoms (torch.topk raises in the
+    reference, models/common.py:176): both are refused at bind time with a message, never truncated silently."""
+    from targetdiff_b200._lib import TdiffError
+    model, _ = _model(2, {'cutoff_mode': 'hybrid'})
+    b = synth.make_batch(9, 1, n_protein=70, ligand_sizes=[34])                  # 32 + 34 - 1 = 65 slots
+    with pytest.raises(TdiffError, match='hybrid'):
+        model(*_args(b))
+    b = synth.make_batch(9, 1, n_protein=20, ligand_sizes=[5])                   # fewer protein atoms than k
+    with pytest.raises(TdiffError, match='hybrid'):
+        model(*_args(b))
+    b = synth.make_batch(9, 1, n_protein=70, ligand_sizes=[33])                  # exactly 64 slots: accepted
+    out = model(*_args(b))
+    assert out['edge_index'].shape[1] == 70 * 32 + 33 * 64

@@ -130,12 +130,13 @@ def test_sampling_chain_noise_mean_type_bit_exact():
 
 
 OPTION_CONFIGS = [{'num_blocks': 2}, {'ew_net_type': 'r'}, {'ew_net_type': 'm'}, {'ew_net_type': 'none'}, {'x2h_out_fc': True},
-                  {'time_emb_dim': 1, 'time_emb_mode': 'simple'}, {'num_blocks': 2, 'ew_net_type': 'r', 'x2h_out_fc': True, 'time_emb_dim': 1}]
+                  {'time_emb_dim': 1, 'time_emb_mode': 'simple'}, {'num_blocks': 2, 'ew_net_type': 'r', 'x2h_out_fc': True, 'time_emb_dim': 1},
+                  {'cutoff_mode': 'hybrid'}, {'cutoff_mode': 'hybrid', 'knn': 8, 'num_blocks': 2}]
 
 
 @pytest.mark.parametrize('cfgd', OPTION_CONFIGS, ids=lambda c: ','.join('%s=%s' % kv for kv in c.items()))
 def test_backbone_options_restatement_bit_exact(cfgd):
-    """num_blocks > 1, ew_net_type r / m / none, x2h_out_fc, time_emb_mode 'simple' -- state_dict layout (key order and
+    """num_blocks > 1, ew_net_type r / m / none, x2h_out_fc, time_emb_mode 'simple', cutoff_mode 'hybrid' -- state_dict layout (key order and
     shapes) and a 3-step sampling chain of the restatement against the unmodified reference, bit for bit."""
     ref = refload.import_reference()
     cfg = refload.default_model_config()

@@ -12,8 +12,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OBJ = os.path.join(CSRC, 'build')
-LIB = os.path.join(HERE, 'libtdiff.so')
+# TDIFF_VARIANT=<name> (developer switch, with TDIFF_NVCC_EXTRA): objects in csrc/build_<name>, library libtdiff_<name>.so -- load it with
+# TDIFF_LIB=... for an A/B of two kernel builds in one GPU call
+_VARIANT = os.environ.get('TDIFF_VARIANT', '')
+OBJ = os.path.join(CSRC, 'build' + ('_' + _VARIANT if _VARIANT else ''))
+LIB = os.path.join(HERE, 'libtdiff%s.so' % ('_' + _VARIANT if _VARIANT else ''))
 SOURCES = ['engine.cu', 'knn.cu', 'edge_const.cu', 'node_ops.cu', 'edge_mlp.cu', 'edge_mlp_tc.cu', 'edge_mlp_v4.cu', 'aggregate.cu', 'sampler.cu', 'stability.cu']
 HEADERS = ['tdiff_common.cuh', 'sampler.cuh', os.path.join('..', '..', 'include', 'tdiff.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',

@@ -189,7 +189,14 @@ edge_mlp_tc_kernel(const float* __restrict__ P, const float4* __restrict__ xm, c
   const uint32_t bar_a_full = smem_u32(bars), bar_a_empty = smem_u32(bars + NBUF), bar_d_full = smem_u32(bars + 2 * NBUF),
                  bar_d_empty = smem_u32(bars + 2 * NBUF + 2);
 
+  // the warp index is broadcast from lane 0 so that the compiler KNOWS it is warp-uniform: role branches become uniform branches and
+  // every constant-bank read indexed by it (LayerNorm parameters, biases) goes through the uniform datapath (LDCU + UR operands)
+  // instead of per-thread LDC into vector registers
+#ifdef TDIFF_PLAIN_WARP_INDEX          // A/B switch (tools/build_variant.sh): the pre-change form, per-thread LDC
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#else
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+#endif
   // ---- one-time setup: weights image -> smem, params, barriers, TMEM
   constexpr int kThreads = (kProdWarp0 + kProdWarps * NSETS) * 32;
   static_assert(NBUF >= NSETS, "every producer set needs its own activation buffer");

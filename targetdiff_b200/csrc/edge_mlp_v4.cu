@@ -232,7 +232,14 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
   const uint32_t sbase = smem_u32(smem_raw);
   const uint32_t sW = sbase + oW, sG = sbase + oG, sT = sbase + oT, sS = sbase + oS, sX = sbase + oX, sBar = sbase + oBar;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem_raw + oBar + 16 * 8);
+  // the warp index is broadcast from lane 0 so that the compiler KNOWS it is warp-uniform: role branches become uniform branches and
+  // every constant-bank read indexed by it (LayerNorm parameters, biases) goes through the uniform datapath (LDCU + UR operands)
+  // instead of per-thread LDC into vector registers
+#ifdef TDIFF_PLAIN_WARP_INDEX          // A/B switch (tools/build_variant.sh): the pre-change form, per-thread LDC
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#else
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+#endif
   auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
   // row -> (destination slot, neighbour slot): k is a power of two for every shipped configuration but 48
   const int kshift = (k & (k - 1)) == 0 ? __ffs(k) - 1 : -1;

@@ -99,6 +99,14 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One elected lane of a converged warp.  Unlike `lane == 0`, the compiler knows that a branch on elect.sync is single-threaded: the
+// uniform-datapath instructions under it (tcgen05.mma, tcgen05.commit) are issued back to back instead of inside a per-lane election
+// loop (6 instructions per MMA) -- the MMA-issuing warp is the one the row threads wait for.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
@@ -217,14 +225,46 @@ __device__ __forceinline__ void split2(float y0, float y1, uint32_t& hi, uint32_
 
 }  // namespace v4
 
+// In-situ wait accounting (variant build only: TDIFF_NVCC_EXTRA=-DTDIFF_WAIT_STATS, tools/wait_stats.py): SM clock cycles the roles
+// spend in their mbarrier waits, summed over every edge_mlp_v4 launch since the last reset.  Slots: 0 row loop total, 1 row S_FULL,
+// 2 row DPRE_FULL, 3 row A_EMPTY, 4 gather loop total, 5 gather S_EMPTY, 6 gather copy (issue + cp.async completion),
+// 7 MMA warp G_FULL, 8 MMA warp D_EMPTY + A_FULL, 9 epilogue loop total, 10 epilogue D_FULL, 11-13 warp loops counted (row, gather,
+// epilogue), 14 MMA warp loop total, 15 MMA warp S_EMPTY
+#ifdef TDIFF_WAIT_STATS
+__device__ unsigned long long g_wait_stats[16];
+#define WS_DECL(n) unsigned ws_##n = 0
+#define WS_T0() const unsigned ws_c0 = (unsigned)clock()
+#define WS_ADD(n) ws_##n += (unsigned)clock() - ws_c0
+#define WS_FLUSH(slot, n) do { if (lane == 0) atomicAdd(&g_wait_stats[slot], (unsigned long long)ws_##n); } while (0)
+extern "C" __attribute__((visibility("default"))) int tdiff_debug_wait_stats(unsigned long long* out16, int reset) {
+  if (out16 && cudaMemcpyFromSymbol(out16, g_wait_stats, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(g_wait_stats, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+#else
+#define WS_DECL(n)
+#define WS_T0()
+#define WS_ADD(n)
+#define WS_FLUSH(slot, n)
+#endif
+
 using namespace v4;
+
+#ifdef TDIFF_LANE0_MMA           // A/B switch: the pre-change form
+#define MMA_LANE (lane == 0)
+#else
+#define MMA_LANE elect_one()
+#endif
 
 // NOUT = 128: key / value MLPs (hk, hv, xk);  NOUT = 16: the per-head scalar value MLP of h2x (xv).
 // Rows: idx = a * k + j over the destination list `row_nodes` (a < n_dst; entries < 0 are padding), edge slot e = row_nodes[a] * k + j.
 // Tiles below `split` destinations are protein-destination tiles (class table 0), the others ligand-destination tiles (table 1).
 template <int NOUT>
 __global__ void __launch_bounds__(kThreads, 1)
-edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, const unsigned char* __restrict__ etype,
+edge_mlp_v4_kernel(const float* __restrict__ P, int zero_row, const int* __restrict__ src, const unsigned char* __restrict__ etype,
                    const float* __restrict__ dist_arr, const int* __restrict__ row_nodes, long long n_dst, long long split_dst,
                    const int* __restrict__ d_counts, int k, int offA, int offB, const unsigned char* __restrict__ w2_image,
                    const unsigned char* __restrict__ tab_image, float coeff, const float* __restrict__ qnode, float* __restrict__ out, int out_by_slot, AggArgs agg, const __grid_constant__ LnParams lp) {
@@ -348,6 +388,10 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
     load_md(0, s0, t0, d0, dist0);
     if (my_tiles > 0) write_g(s0, t0, dist0);
     load_md(1, s1, t1, d1, dist1);
+    WS_DECL(rs); WS_DECL(rd); WS_DECL(ra); WS_DECL(rt);
+#ifdef TDIFF_WAIT_STATS
+    const unsigned ws_loop0 = (unsigned)clock();
+#endif
     for (long long it = 0; it < my_tiles; ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
       const bool valid = s0 >= 0;
@@ -360,7 +404,19 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
         if (valid) av[c] = __ldg(reinterpret_cast<const float4*>(P + (size_t)d0 * TD_NPROJ + offA + 32 * qq + 4 * c));
       }
       f2 x[16];
-      mbar_wait(bar(B_S_FULL), ph);
+#ifdef TDIFF_ROW_SLEEP           // A/B switch: back off while waiting for the gather warps instead of spinning beside them
+      { WS_T0();
+        while (true) {
+          uint32_t done;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done) : "r"(bar(B_S_FULL)), "r"(ph) : "memory");
+          if (done) break;
+          __nanosleep(32);
+        }
+        WS_ADD(rs); }
+#else
+      { WS_T0(); mbar_wait(bar(B_S_FULL), ph); WS_ADD(rs); }
+#endif
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const float4 v = lds128(s_row + 16u * c);
@@ -369,7 +425,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_S_EMPTY));
       // ---- + gaussian/type block from the tensor core
-      mbar_wait(bar(B_DPRE_FULL), ph);
+      { WS_T0(); mbar_wait(bar(B_DPRE_FULL), ph); WS_ADD(rd); }
       tc_fence_after();
       {
         uint32_t v0[16], v1[16];
@@ -425,7 +481,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
           split2(fmaxf(y2, 0.f), fmaxf(y3, 0.f), hi[2 * c + 1], lo[2 * c + 1]);
         }
       }
-      mbar_wait(bar(B_A_EMPTY), ph ^ 1u);         // the previous tile's MMAs have read A
+      { WS_T0(); mbar_wait(bar(B_A_EMPTY), ph ^ 1u); WS_ADD(ra); }         // the previous tile's MMAs have read A
       tc_fence_after();
       tmem_st16(t_lane + kColA + (uint32_t)(16 * qq), hi);
       tmem_st16(t_lane + kColA + 64u + (uint32_t)(16 * qq), lo);
@@ -434,6 +490,11 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_A_FULL));
     }
+#ifdef TDIFF_WAIT_STATS
+    ws_rt = (unsigned)clock() - ws_loop0;
+    WS_FLUSH(0, rt); WS_FLUSH(1, rs); WS_FLUSH(2, rd); WS_FLUSH(3, ra);
+    if (lane == 0) atomicAdd(&g_wait_stats[11], 1ull);
+#endif
   } else if (warp >= kGatherWarp0) {
     // ================================================================= gather warps (lane = 4 features), 32 rows each; the last one
     //                                                                   also issues the MMAs (one thread) between its copies
@@ -461,8 +522,9 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       return s_;
     };
     // Dpre = G(t) . TabClass^T   (K = 64: four K=16 instructions per product term)
+    WS_DECL(gs); WS_DECL(gc); WS_DECL(gg); WS_DECL(gm); WS_DECL(gt);
     auto issue_pre = [&](long long t) {
-      mbar_wait(bar(B_G_FULL), (uint32_t)(t & 1));       // every row warp has written G(t), i.e. has also read Dpre(t-1): sT is idle
+      { WS_T0(); mbar_wait(bar(B_G_FULL), (uint32_t)(t & 1)); WS_ADD(gg); }       // every row warp has written G(t), i.e. has also read Dpre(t-1): sT is idle
       tc_fence_after();
       const int cls = tile_class(t);
       if (t == 0) mbar_wait(bar(B_LOAD), 0);              // W2 pieces and the first class table have landed
@@ -475,7 +537,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
         cur_class = cls;
         __syncwarp();
       }
-      if (lane == 0) {
+      if (MMA_LANE) {
         const uint32_t d_addr = tmem_base + kColDpre;
         uint32_t accum = 0;
 #pragma unroll
@@ -494,10 +556,10 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
     // D[t&1] = A(t) . W2^T, A pieces in tensor memory
     auto issue_main = [&](long long t) {
       const uint32_t ph = (uint32_t)(t & 1), ph2 = (uint32_t)((t >> 1) & 1);
-      mbar_wait_relaxed(bar(B_D_EMPTY0 + (int)ph), ph2 ^ 1u);
-      mbar_wait(bar(B_A_FULL), ph);
+      { WS_T0(); mbar_wait_relaxed(bar(B_D_EMPTY0 + (int)ph), ph2 ^ 1u);
+        mbar_wait(bar(B_A_FULL), ph); WS_ADD(gm); }
       tc_fence_after();
-      if (lane == 0) {
+      if (MMA_LANE) {
         const uint32_t d_addr = tmem_base + kColD + ph * 128u;
         uint32_t accum = 0;
 #pragma unroll
@@ -516,12 +578,35 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       __syncwarp();
     };
     int s0 = load_md(0);
+#ifdef TDIFF_WAIT_STATS
+    const unsigned ws_loop0 = (unsigned)clock();
+#endif
     // iteration `it`: copy S(it) (overlaps the row threads' work on tile it-1), then Dpre(it), then the main MMA of tile it-1
     for (long long it = 0; it <= my_tiles; ++it) {
       if (it < my_tiles) {
         const int s1 = load_md(it + 1);                      // next tile's metadata lands while this tile's rows are copied
-        mbar_wait(bar(B_S_EMPTY), (uint32_t)((it & 1) ^ 1));
+#ifdef TDIFF_PRE_FIRST          // A/B switch (measured: no gain): the small MMA before this warp's copies instead of after them
+        if (mma_warp) issue_pre(it);
+#endif
+        { WS_T0(); mbar_wait(bar(B_S_EMPTY), (uint32_t)((it & 1) ^ 1)); WS_ADD(gs); }
+#ifdef TDIFF_WAIT_STATS
+        const unsigned ws_copy0 = (unsigned)clock();
+#endif
         // ---- P[src_row, offB + 4*lane ..] -> S, 32 rows x 512 B per warp, asynchronously (no registers, L2 -> shared)
+#ifndef TDIFF_BRANCHY_GATHER
+        // absent neighbour slots read the all-zero row `zero_row` of P (kept by the engine): no per-row predicate or zero store, and the
+        // fully unrolled loop shuffles with constant lane numbers -- 6 instead of 9 issue slots per row for the warp the row threads wait on
+        {
+          const unsigned sg = (unsigned)(s0 >= 0 ? s0 : zero_row);
+          const float* pl = P + offB + 4 * lane;
+          const uint32_t dst0 = sS + (uint32_t)atom * kSAtom + (uint32_t)(32 * gw) * kSRow + (uint32_t)(ch << 4);
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const unsigned sr = __shfl_sync(0xffffffffu, sg, rr);
+            cp_async16(dst0 + (uint32_t)rr * kSRow, pl + (size_t)sr * TD_NPROJ);
+          }
+        }
+#else                      // A/B switch: the per-row branch form measured before this change
 #pragma unroll 8
         for (int rr = 0; rr < 32; ++rr) {
           const int row = 32 * gw + rr;
@@ -530,18 +615,34 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
           if (sr >= 0) cp_async16(dsta, P + (size_t)sr * TD_NPROJ + offB + 4 * lane);
           else sts128f(dsta, make_float4(0.f, 0.f, 0.f, 0.f));
         }
+#endif
         cp_async_wait_all();
         __syncwarp();
+#ifdef TDIFF_WAIT_STATS
+        ws_gc += (unsigned)clock() - ws_copy0;
+#endif
         if (lane == 0) mbar_arrive(bar(B_S_FULL));
         s0 = s1;
+#ifndef TDIFF_PRE_FIRST
         if (mma_warp) issue_pre(it);
+#endif
       }
       if (mma_warp && it >= 1) issue_main(it - 1);
     }
+#ifdef TDIFF_WAIT_STATS
+    ws_gt = (unsigned)clock() - ws_loop0;
+    WS_FLUSH(4, gt); WS_FLUSH(5, gs); WS_FLUSH(6, gc); WS_FLUSH(7, gg); WS_FLUSH(8, gm);
+    if (lane == 0) atomicAdd(&g_wait_stats[12], 1ull);
+    if (mma_warp) { WS_FLUSH(14, gt); WS_FLUSH(15, gs); }
+#endif
   } else {
     // ================================================================= epilogue: warp w <-> TMEM lanes 32 (w%4) .., columns 64 (w/4) ..
     const int eq = warp & 3;
     const int HALF = warp >> 2;                    // one code copy for both column halves (b2 through indexed constant loads)
+    WS_DECL(ed); WS_DECL(et);
+#ifdef TDIFF_WAIT_STATS
+    const unsigned ws_loop0 = (unsigned)clock();
+#endif
     for (long long it = 0; it < my_tiles; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const uint32_t ph = (uint32_t)(it & 1), ph2 = (uint32_t)((it >> 1) & 1);
@@ -599,7 +700,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       // output row of the non-fused paths: the row index itself, or the edge slot (consumers that index by node * k + j)
       const long long orow = out_by_slot ? ((long long)dst * k + jj) : idx;
       const bool owrite = idx < n_rows && dst >= 0;
-      mbar_wait_relaxed(bar(B_D_FULL0 + (int)ph), ph2);
+      { WS_T0(); mbar_wait_relaxed(bar(B_D_FULL0 + (int)ph), ph2); WS_ADD(ed); }
       tc_fence_after();
       if (NOUT == 16) {
         // ---- xv: out[row, 0:16] = D[:, 0:16] + b2   (first column half only)
@@ -703,6 +804,11 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_D_EMPTY0 + (int)ph));
     }
+#ifdef TDIFF_WAIT_STATS
+    ws_et = (unsigned)clock() - ws_loop0;
+    WS_FLUSH(9, et); WS_FLUSH(10, ed);
+    if (lane == 0) atomicAdd(&g_wait_stats[13], 1ull);
+#endif
   }
   // ---- teardown
   tc_fence_before();
@@ -714,7 +820,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, const int* __restrict__ src, con
 }
 
 // n_dst destinations (device counts {n_dst, split_dst} in d_counts override the host values); see the kernel comment for the row model
-void td_launch_edge_mlp_v4(const float* P, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_dst,
+void td_launch_edge_mlp_v4(const float* P, int zero_row, const int* src, const unsigned char* etype, const float* dist, const int* row_nodes, long long n_dst,
                            long long split_dst, const int* d_counts, int k, const TdMlp& m, const float* h_offsets, float coeff,
                            const float* h_ln_g, const float* h_ln_b, const float* h_b2, const float* qnode, float* out, int out_by_slot,
                            const float* agg_logits, const float* agg_e_w, float* agg_h, int key_softmax, int sm_count, cudaStream_t st) {
@@ -732,9 +838,9 @@ void td_launch_edge_mlp_v4(const float* P, const int* src, const unsigned char* 
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
   AggArgs agg = {agg_logits, agg_e_w, agg_h, (key_softmax && k == 32) ? 1 : 0};
   if (m.nout == 16)
-    edge_mlp_v4_kernel<16><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_dst, split_dst, d_counts, k, m.offA, m.offB, m.w2_img,
+    edge_mlp_v4_kernel<16><<<grid, kThreads, kSmem, st>>>(P, zero_row, src, etype, dist, row_nodes, n_dst, split_dst, d_counts, k, m.offA, m.offB, m.w2_img,
                                                          m.tabcls_img, coeff, nullptr, out, out_by_slot, agg, lp);
   else
-    edge_mlp_v4_kernel<128><<<grid, kThreads, kSmem, st>>>(P, src, etype, dist, row_nodes, n_dst, split_dst, d_counts, k, m.offA, m.offB, m.w2_img,
+    edge_mlp_v4_kernel<128><<<grid, kThreads, kSmem, st>>>(P, zero_row, src, etype, dist, row_nodes, n_dst, split_dst, d_counts, k, m.offA, m.offB, m.w2_img,
                                                           m.tabcls_img, coeff, qnode, out, out_by_slot, agg, lp);
 }

@@ -587,7 +587,7 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   bad |= e->node_ptr.ensure((B + 1) * 4) | e->prot_ptr.ensure((B + 1) * 4) | e->prot_node.ensure(Np * 4 + 4) | e->prot_graph.ensure(Np * 4 + 4);
   bad |= e->lig_node.ensure(Nl * 4 + 4) | e->lig_graph.ensure(Nl * 4 + 4) | e->node_lig.ensure(N * 4);
   bad |= e->xm0.ensure(N * 16) | e->xm1.ensure(N * 16) | e->offset.ensure((size_t)B * 16);
-  bad |= e->h0.ensure(N * TD_H * 4) | e->h.ensure(N * TD_H * 4) | e->P.ensure((size_t)N * TD_NPROJ * 4) | e->q.ensure(N * TD_H * 4);
+  bad |= e->h0.ensure(N * TD_H * 4) | e->h.ensure(N * TD_H * 4) | e->P.ensure((size_t)(N + 1) * TD_NPROJ * 4) | e->q.ensure(N * TD_H * 4);
   bad |= e->src.ensure(slots * 4) | e->src_prev.ensure(slots * 4) | e->etype.ensure(slots) | e->e_w.ensure(slots * 4) | e->dist.ensure(slots * 4);
   // class-sorted destination lists (v4 edge kernel): each class padded so that its rows end on a 128-row tile boundary
   const bool v4 = e->mlp_mode == 2 && e->mlp_v4;
@@ -649,6 +649,8 @@ extern "C" int tdiff_bind_batch(tdiff_engine* e, int B, const int32_t* pc, const
   CK(cudaMemsetAsync(e->xm0.p, 0, (size_t)N * 16, st));
   CK(cudaMemsetAsync(e->xm1.p, 0, (size_t)N * 16, st));
   CK(cudaMemsetAsync(e->etype.p, 0, slots, st));            // bit 7 of an edge type is the "keep" mark of the incremental edge gate
+  // row N of the projection table stays all-zero: the edge kernel's gather warps read it for absent neighbour slots (no per-row branch)
+  CK(cudaMemsetAsync(e->P.as<float>() + (size_t)N * TD_NPROJ, 0, (size_t)TD_NPROJ * 4, st));
   if (center_mode == 1) td_launch_segment_mean3(d_ppos, e->prot_ptr.as<int>(), B, e->offset.as<float4>(), st);
   td_launch_place_protein(d_ppos, e->prot_node.as<int>(), e->prot_graph.as<int>(), e->offset.as<float4>(), (int)Np, e->xm0.as<float4>(),
                           e->xm1.as<float4>(), st);
@@ -736,7 +738,7 @@ void edge_mlp(tdiff_engine* e, const float* P, const float4* xm, const int* src,
     const long long split = list == ROWS_LIGAND ? 0 : e->x2h_split;
     // plain (unfused) x2h outputs are consumed by slot index (aggregate_h_logits_kernel); everything else by row index
     const int by_slot = (list != ROWS_LIGAND && !key_softmax && agg_logits == nullptr) ? 1 : 0;
-    td_launch_edge_mlp_v4(P, src, etype, e->dist.as<float>(), rows, n_dst, split, counts, K, m,
+    td_launch_edge_mlp_v4(P, e->N, src, etype, e->dist.as<float>(), rows, n_dst, split, counts, K, m,
                           e->host_arena.data() + (offsets - e->arena), coeff, e->host_arena.data() + (m.ln_g - e->arena), e->host_arena.data() + (m.ln_b - e->arena),
                           e->host_arena.data() + (m.b2 - e->arena), qnode, out, by_slot, agg_logits, e_w, agg_h, key_softmax,
                           e->sm_count, st);

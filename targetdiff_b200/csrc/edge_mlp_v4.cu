@@ -768,6 +768,17 @@ edge_mlp_v4_kernel(const float* __restrict__ P, int zero_row, const int* __restr
           for (int hh = 0; hh < 2; ++hh) {
             const float* bb = lp.b2 + 64 * HALF + c0 + 8 * hh;
             const float4 qa = qv[2 * hh], qb = qv[2 * hh + 1];
+#ifdef TDIFF_PACKED_LOGITS        // A/B switch (measured -0.2 %, i.e. nothing: not shipped, its rounding order differs from the validated build)
+            // packed fp32 pairs: even and odd feature of the head accumulate separately (4 dependent FFMA2 instead of 8 dependent FFMA)
+            const uint32_t* vv = v + 8 * hh;
+            f2 acc = mul2(add2(pk2(__uint_as_float(vv[0]), __uint_as_float(vv[1])), pk2(bb[0], bb[1])), pk2(qa.x, qa.y));
+            acc = fma2(add2(pk2(__uint_as_float(vv[2]), __uint_as_float(vv[3])), pk2(bb[2], bb[3])), pk2(qa.z, qa.w), acc);
+            acc = fma2(add2(pk2(__uint_as_float(vv[4]), __uint_as_float(vv[5])), pk2(bb[4], bb[5])), pk2(qb.x, qb.y), acc);
+            acc = fma2(add2(pk2(__uint_as_float(vv[6]), __uint_as_float(vv[7])), pk2(bb[6], bb[7])), pk2(qb.z, qb.w), acc);
+            float s_even, s_odd;
+            upk2(acc, s_even, s_odd);
+            lg[c0 / 8 + hh] = (s_even + s_odd) * 0.35355339059327373f;          // 1/sqrt(8)
+#else
             float sacc = (__uint_as_float(v[8 * hh]) + bb[0]) * qa.x;
             sacc = fmaf(__uint_as_float(v[8 * hh + 1]) + bb[1], qa.y, sacc);
             sacc = fmaf(__uint_as_float(v[8 * hh + 2]) + bb[2], qa.z, sacc);
@@ -777,6 +788,7 @@ edge_mlp_v4_kernel(const float* __restrict__ P, int zero_row, const int* __restr
             sacc = fmaf(__uint_as_float(v[8 * hh + 6]) + bb[6], qb.z, sacc);
             sacc = fmaf(__uint_as_float(v[8 * hh + 7]) + bb[7], qb.w, sacc);
             lg[c0 / 8 + hh] = sacc * 0.35355339059327373f;          // 1/sqrt(8)
+#endif
           }
         }
         if (key_sm) {

@@ -272,28 +272,26 @@ def test_incremental_knn_equals_full_scan(monkeypatch):
     assert torch.equal(torch.stack(res[0][0]['pos_traj']), torch.stack(res[1][0]['pos_traj']))
 
 
-@pytest.mark.skipif(not __import__('os').environ.get('TDIFF_TEST_EXPERIMENTAL'),
-                    reason='experimental kernels (off by default) are validated on demand: TDIFF_TEST_EXPERIMENTAL=1')
-def test_experimental_slow_tc_vs_oracle(monkeypatch):
-    """TDIFF_SLOW_TC=1: rare-type gaussian block on tensor cores instead of edge_slow_kernel.  Forward and a short
-    chain against the oracle; with `timeout` around the pytest call when first enabled -- the kernel has never run on a GPU."""
-    monkeypatch.setenv('TDIFF_SLOW_TC', '1')
-    model, sd = _model(1)
-    b = synth.make_batch(31, 3, n_protein=150, ligand_sizes=[20, 1, 33])
-    pp, lp, _ = restate.center_pos(b['protein_pos'], b['init_ligand_pos'], b['batch_protein'], b['batch_ligand'])
-    tr = {}
-    want = restate.forward(sd, None, pp, b['protein_v'], b['batch_protein'], lp, b['init_ligand_v'], b['batch_ligand'], trace=tr)
-    out = model(pp.to(DEV), b['protein_v'].to(DEV), b['batch_protein'].to(DEV), lp.to(DEV), b['init_ligand_v'].to(DEV), b['batch_ligand'].to(DEV))
-    assert torch.equal(out['edge_index'].cpu(), tr['edge_index'])
-    torch.testing.assert_close(out['pred_ligand_pos'].cpu(), want['pred_ligand_pos'], rtol=1e-4, atol=1e-5)
-    torch.testing.assert_close(out['pred_ligand_v'].cpu(), want['pred_ligand_v'], rtol=0, atol=1e-3)
-    torch.testing.assert_close(out['final_h'].cpu(), want['final_h'], rtol=1e-4, atol=1e-4)
-    S = 4
-    pn, vu = synth.make_tape(7, S, len(b['batch_ligand']))
-    want = restate.sample_diffusion(sd, None, *_args(b, 'cpu'), pn, vu, num_steps=S)
-    got = model.sample_diffusion(*_args(b), num_steps=S, center_pos_mode='protein', noise_tape=(pn, vu))
-    assert torch.equal(torch.stack(got['v_traj']), torch.stack(want['v_traj']))
-    torch.testing.assert_close(torch.stack(got['pos_traj']), torch.stack(want['pos_traj']), rtol=1e-4, atol=1e-4)
+def test_hybrid_incremental_knn_equals_full_scan(monkeypatch):
+    """cutoff_mode='hybrid' (reference models/common.py:165-212) through both neighbour-list builders: the incremental one (cached
+    protein keys + per-step merge for protein rows, `hybrid_ligand_row` for ligand rows) and the full per-step scan (TDIFF_KNN_FULL=1)
+    must give bit-identical graphs and chains.  Ragged ligands incl. a single-atom one (its row: no ligand neighbour, k protein atoms)."""
+    cfg = {'cutoff_mode': 'hybrid', 'knn': 24}
+    b = synth.make_batch(12, 4, n_protein=90, ligand_sizes=[20, 1, 33, 7])
+    S = 6
+    pn, vu = synth.make_tape(3, S, int(b['init_ligand_pos'].shape[0]))
+    res = []
+    for full in ('', '1'):
+        if full:
+            monkeypatch.setenv('TDIFF_KNN_FULL', full)
+        model, _ = _model(2, cfg)
+        out = model.sample_diffusion(*_args(b), num_steps=S, center_pos_mode='protein', noise_tape=(pn, vu))
+        fwd = model(*_args(b))
+        res.append((out, fwd['edge_index']))
+    assert res[0][1].shape[1] == 4 * 90 * 24 + sum(n * (n - 1 + 24) for n in (20, 1, 33, 7))
+    assert torch.equal(res[0][1], res[1][1])
+    assert torch.equal(res[0][0]['pos'], res[1][0]['pos']) and torch.equal(res[0][0]['v'], res[1][0]['v'])
+    assert torch.equal(torch.stack(res[0][0]['pos_traj']), torch.stack(res[1][0]['pos_traj']))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs in one process')

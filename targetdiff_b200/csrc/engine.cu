@@ -468,9 +468,9 @@ extern "C" int tdiff_create(const tdiff_config* cfg, const tdiff_tensor* sd, int
     else if (!strcmp(mode, "tc6")) e->mlp_mode = 3;
     else { cudaFree(e->arena); cudaFree(e->img_arena); delete e; return set_err(TDIFF_EINVAL, "TDIFF_EDGE_MLP=%s (simt|tc3|tc3v2|tc6)", mode); }
   }
-  if ((cfg->ew_net_type != 0 || cfg->x2h_out_fc) && !(e->mlp_mode == 2 && e->mlp_v4)) {
+  if ((cfg->ew_net_type != 0 || cfg->x2h_out_fc || cfg->cutoff_mode != 0) && !(e->mlp_mode == 2 && e->mlp_v4)) {
     cudaFree(e->arena); cudaFree(e->img_arena); delete e;
-    return set_err(TDIFF_EINVAL, "ew_net_type != 'global' and x2h_out_fc are implemented by the default engine mode only (unset TDIFF_EDGE_MLP)");
+    return set_err(TDIFF_EINVAL, "ew_net_type != 'global', x2h_out_fc and cutoff_mode 'hybrid' are implemented (and tested) in the default engine mode only (unset TDIFF_EDGE_MLP)");
   }
   e->env_no_fused_agg = getenv("TDIFF_NO_FUSED_AGG") != nullptr;
   e->env_no_restrict = getenv("TDIFF_NO_RESTRICT") != nullptr;
